@@ -1,0 +1,173 @@
+// Shared device code of the SOT hot path: flat-tree scans and canonical class ids.
+//
+// Reference semantics restated here (boschresearch/bosot, bosot/kernels/kernel_grammar/kernel_grammar.py):
+//   * structural class of a subtree = (operator, unordered {class(left), class(right)}),
+//     leaf class = its base-kernel symbol                       (get_hash, :268-271, :452-470)
+//   * reduced leaf->root operator path: consecutive equal operators collapse, so a
+//     path is fully described by (length, operator nearest to the leaf)
+//                                                               (:624-658, :683-696, :216-220)
+// The reference identifies classes by salted Python hash(); only the induced partition
+// is portable, so classes are identified here by a 64-bit mix of the canonical triple.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/bosot_b200.h"
+
+namespace bosot {
+
+constexpr int kTreeBytes = BOSOT_TREE_BYTES;
+constexpr int kMaxNodes = BOSOT_MAX_NODES;
+constexpr int kMaxLeaves = BOSOT_MAX_LEAVES;
+constexpr int kMaxInternal = BOSOT_MAX_INTERNAL;
+constexpr int kPathCodes = BOSOT_PATH_CODES;
+
+// Per-tree working record in shared memory.  Stride 424 B = 8 * 53 (odd multiple of 8):
+// 64-bit accesses of 32 threads working on 32 different trees spread over all banks,
+// and a warp working on ONE tree reads consecutive ids / bytes.
+constexpr int kRecIid = 0;        // uint64 iid[31]   class ids of internal nodes (by reverse pre-order rank)
+constexpr int kRecTok = 248;      // uint8  raw record: n, tokens (64 B)
+constexpr int kRecStack = 312;    // uint8  stack[32] scratch of the two scans
+constexpr int kRecLeafSym = 344;  // uint8  leaf_sym[32]   leaves in pre-order (left to right)
+constexpr int kRecLeafCode = 376; // uint8  leaf_code[32]  reduced path code per leaf
+constexpr int kRecMeta = 408;     // uint8  n_nodes, n_leaves, n_internal, status
+constexpr int kRecBytes = 424;
+
+__device__ __forceinline__ uint64_t fmix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xff51afd7ed558ccdULL;
+  x ^= x >> 33;
+  x *= 0xc4ceb9fe1a85ec53ULL;
+  x ^= x >> 33;
+  return x;
+}
+
+// Canonical id of an operator node from its operator (1 = ADD, 2 = MULTIPLY) and the ids of
+// its children; symmetric in the children (commutative class), bit 63 always set so that
+// it can never equal a leaf id (symbol + 1 <= 64).
+__device__ __forceinline__ uint64_t class_combine(uint32_t op, uint64_t a, uint64_t b) {
+  const uint64_t lo = a < b ? a : b;
+  const uint64_t hi = a < b ? b : a;
+  uint64_t x = fmix64(lo * 0x9E3779B97F4A7C15ULL + op);
+  x = fmix64((x ^ hi) * 0xC2B2AE3D27D4EB4FULL + 0x165667B19E3779F9ULL);
+  return x | 0x8000000000000000ULL;
+}
+
+__device__ __forceinline__ uint64_t leaf_class(uint32_t sym) { return (uint64_t)sym + 1; }
+
+// Path-code transition: state of the children of an operator node with operator bit `o`
+// (0 ADD, 1 MULTIPLY) whose own state is `cur` (0 = root / empty path).
+__device__ __forceinline__ uint32_t path_child_code(uint32_t cur, uint32_t o) {
+  if (cur != 0 && ((cur - 1) & 1) == o) return cur;  // same operator as the one above: run collapses
+  const uint32_t len = cur == 0 ? 0 : ((cur - 1) >> 1) + 1;
+  return 1 + 2 * len + o;
+}
+
+// One thread scans one tree record (already copied to rec + kRecTok).
+// Backward pass over the pre-order tokens = stack evaluation -> class id of every operator
+// node; forward pass = top-down propagation of the reduced-path state -> (symbol, code) of
+// every leaf.  Writes meta bytes; returns 0 or a BOSOT_TREE_* defect code.
+__device__ __forceinline__ int scan_tree(uint8_t* rec, int n_symbols) {
+  uint64_t* iid = reinterpret_cast<uint64_t*>(rec + kRecIid);
+  const uint8_t* tok = rec + kRecTok + 1;
+  uint8_t* st = rec + kRecStack;
+  uint8_t* lsym = rec + kRecLeafSym;
+  uint8_t* lcode = rec + kRecLeafCode;
+  const int n = rec[kRecTok];
+  int status = 0;
+  int n_int = 0, n_leaf = 0;
+  if (n < 1 || n > kMaxNodes || !(n & 1)) {
+    status = BOSOT_TREE_BAD_LENGTH;
+  } else {
+    int sp = 0;
+    for (int i = n - 1; i >= 0; --i) {
+      const uint32_t t = tok[i];
+      if (t < 0x80) {
+        if ((int)t >= n_symbols) { status = BOSOT_TREE_BAD_TOKEN; break; }
+        if (sp >= kMaxLeaves) { status = BOSOT_TREE_BAD_SHAPE; break; }
+        st[sp++] = (uint8_t)t;
+      } else {
+        if (t > BOSOT_OP_MUL) { status = BOSOT_TREE_BAD_TOKEN; break; }
+        if (sp < 2 || n_int >= kMaxInternal) { status = BOSOT_TREE_BAD_SHAPE; break; }
+        const uint32_t a = st[sp - 1], b = st[sp - 2];
+        sp -= 2;
+        const uint64_t ia = (a & 0x80) ? iid[a & 0x7f] : leaf_class(a);
+        const uint64_t ib = (b & 0x80) ? iid[b & 0x7f] : leaf_class(b);
+        iid[n_int] = class_combine(t - 0x7f, ia, ib);
+        st[sp++] = (uint8_t)(0x80 | n_int);
+        ++n_int;
+      }
+    }
+    if (status == 0 && sp != 1) status = BOSOT_TREE_BAD_SHAPE;
+    if (status == 0) {
+      sp = 0;
+      uint32_t cur = 0;
+      for (int i = 0; i < n; ++i) {
+        const uint32_t t = tok[i];
+        if (t >= 0x80) {
+          cur = path_child_code(cur, t & 1);
+          st[sp++] = (uint8_t)cur;  // pending right child inherits the same state
+        } else {
+          lsym[n_leaf] = (uint8_t)t;
+          lcode[n_leaf] = (uint8_t)cur;
+          ++n_leaf;
+          if (sp > 0) cur = st[--sp];
+        }
+      }
+    }
+  }
+  rec[kRecMeta + 0] = (uint8_t)n;
+  rec[kRecMeta + 1] = (uint8_t)n_leaf;
+  rec[kRecMeta + 2] = (uint8_t)n_int;
+  rec[kRecMeta + 3] = (uint8_t)status;
+  return status;
+}
+
+// ---- evaluated-set blob layout (all offsets 16-byte aligned) ---------------------------
+struct EvalLayout {
+  int n_eval;     // E
+  int e_pad;      // E rounded up to 32
+  int hash_cap;   // power of two >= 2 * 31 * E (load factor <= 0.5)
+  int n_slots;    // hash_cap + 64 + 64*64 : unified slot space (hash | leaf symbol | path id)
+  int max_post;   // 95 * E
+  size_t off_keys;     // uint64 [hash_cap]
+  size_t off_range;    // uint2  [n_slots]   (begin, length) into postings
+  size_t off_post;     // uint32 [max_post]  e | count << 16 | total << 24
+  size_t off_nnodes;   // uint8  [e_pad]
+  size_t off_nleaves;  // uint8  [e_pad]
+  size_t off_dimT;     // double [BOSOT_MAX_DIM_COLS][e_pad]  transposed dim-wise matrix
+  size_t off_cursor;   // uint32 [n_slots]   build scratch
+  size_t total;
+};
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+__host__ __device__ inline EvalLayout eval_layout(int n_eval) {
+  EvalLayout L;
+  L.n_eval = n_eval;
+  L.e_pad = (n_eval + 31) & ~31;
+  int cap = 64;
+  while (cap < 2 * kMaxInternal * n_eval) cap <<= 1;
+  L.hash_cap = cap;
+  L.n_slots = cap + BOSOT_MAX_SYMBOLS + BOSOT_MAX_SYMBOLS * kPathCodes;
+  L.max_post = (kMaxInternal + 2 * kMaxLeaves) * n_eval;
+  size_t o = 64;  // header
+  L.off_keys = o;      o = align16(o + sizeof(uint64_t) * (size_t)cap);
+  L.off_range = o;     o = align16(o + sizeof(uint2) * (size_t)L.n_slots);
+  L.off_post = o;      o = align16(o + sizeof(uint32_t) * (size_t)L.max_post);
+  L.off_nnodes = o;    o = align16(o + (size_t)L.e_pad);
+  L.off_nleaves = o;   o = align16(o + (size_t)L.e_pad);
+  L.off_dimT = o;      o = align16(o + sizeof(double) * (size_t)BOSOT_MAX_DIM_COLS * L.e_pad);
+  L.off_cursor = o;    o = align16(o + sizeof(uint32_t) * (size_t)L.n_slots);
+  L.total = o;
+  return L;
+}
+
+__device__ __forceinline__ uint32_t hash_slot(uint64_t id, int cap) {
+  return (uint32_t)(id ^ (id >> 32)) & (uint32_t)(cap - 1);
+}
+
+__device__ __forceinline__ uint32_t pack_posting(uint32_t e, uint32_t cnt, uint32_t total) {
+  return e | (cnt << 16) | (total << 24);
+}
+
+}  // namespace bosot

@@ -1,0 +1,283 @@
+// Fused SOT pair kernel: flat candidate trees -> per-feature L1 distances -> weighted SOT
+// distance -> Gram entries, against the inverted index of the evaluated set.
+//
+// Restates, for every (candidate, evaluated) pair, the reference's
+//   wasserstein_distance(X, X2)   bosot/kernels/kernel_kernel_grammar_tree.py:143-161
+//   manhatten_distance            bosot/utils/utils.py:168-170
+//   K(X, X2)                      bosot/kernels/kernel_kernel_grammar_tree.py:110-113
+// without ever forming the dense [N, F] / [N, M, F] tensors: for histograms normalised to
+// sum 1, sum_k |a_k - b_k| = 2 - 2 * sum_k min(a_k, b_k), and with a_k = ca/Ta, b_k = cb/Tb
+// the sum of minima is the exact integer M = sum_k min(ca*Tb, cb*Ta) over Ta*Tb.  Only
+// features present in BOTH trees contribute, so one candidate costs O(matches), found
+// through the evaluated set's postings, instead of O(E * F).
+//
+// Work decomposition (one warp owns 32 consecutive candidates at a time):
+//   phase A  thread-per-tree : scan_tree() -> class ids, leaf symbols, reduced path codes (smem)
+//   phase B  warp-per-tree   : dedupe with __match_any_sync, look the features up (hash table for
+//                              operator classes, direct tables for leaf symbols and paths),
+//                              walk the postings, accumulate M_sub / M_path per evaluated tree
+//   phase C  lane-per-pair   : DIM_WISE dense L1, combine with the alpha weights, exp, store
+#include "sot_common.cuh"
+#include "launch.cuh"
+
+namespace bosot {
+
+constexpr int kPairWarps = 4;
+constexpr int kPairThreads = kPairWarps * 32;
+
+__constant__ double c_recip[64];  // 1/T for T = 1..63 ([0] unused)
+
+struct PairParams {
+  const uint8_t* trees;
+  int64_t n_cand;
+  const uint8_t* blob;
+  EvalLayout L;
+  double w_dim, w_path, w_sub;
+  double variance, lengthscale_sq;
+  double* K;
+  double* D;
+  double* Df;
+  int64_t ld;
+  int32_t* status;
+};
+
+// per-warp shared memory: 32 tree records, accumulators, candidate dim-wise vector, symbol counts
+__host__ __device__ inline size_t pair_warp_smem(int e_pad) {
+  return (size_t)32 * kRecBytes + sizeof(uint32_t) * (size_t)e_pad + sizeof(double) * BOSOT_MAX_DIM_COLS +
+         sizeof(uint32_t) * (BOSOT_MAX_SYMBOLS + BOSOT_MAX_BLOCKS);
+}
+
+__global__ void __launch_bounds__(kPairThreads)
+sot_pair_kernel(PairParams p, bosot_grammar g) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int E = p.L.n_eval;
+  const int e_pad = p.L.e_pad;
+  const unsigned full = 0xffffffffu;
+
+  uint8_t* wbase = smem + (size_t)warp * pair_warp_smem(e_pad);
+  uint8_t* recs = wbase;                                                   // 32 * 424 B
+  double* avec = reinterpret_cast<double*>(wbase + 32 * kRecBytes);        // candidate DIM_WISE vector
+  uint32_t* acc = reinterpret_cast<uint32_t*>(avec + BOSOT_MAX_DIM_COLS);  // M_sub | M_path << 16 per e
+  uint32_t* scnt = acc + e_pad;                                            // leaf count per symbol
+  uint32_t* btot = scnt + BOSOT_MAX_SYMBOLS;                               // leaf count per block
+
+  const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(p.blob + p.L.off_keys);
+  const uint2* range = reinterpret_cast<const uint2*>(p.blob + p.L.off_range);
+  const uint32_t* post = reinterpret_cast<const uint32_t*>(p.blob + p.L.off_post);
+  const uint8_t* e_nn = p.blob + p.L.off_nnodes;
+  const uint8_t* e_nl = p.blob + p.L.off_nleaves;
+  const double* dimT = reinterpret_cast<const double*>(p.blob + p.L.off_dimT);
+  const int hash_cap = p.L.hash_cap;
+  const int F = g.n_dim_cols;
+
+  const int64_t n_chunks = (p.n_cand + 31) >> 5;
+  for (int64_t chunk = (int64_t)blockIdx.x * kPairWarps + warp; chunk < n_chunks;
+       chunk += (int64_t)gridDim.x * kPairWarps) {
+    const int64_t c0 = chunk << 5;
+    const int in_chunk = (int)min((int64_t)32, p.n_cand - c0);
+
+    // ---- phase A: coalesced load of 32 records (2 KB), then one thread scans one tree
+    __syncwarp();
+    for (int w = lane; w < in_chunk * 4; w += 32) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.trees + c0 * kTreeBytes) + w);
+      *reinterpret_cast<uint4*>(recs + (w >> 2) * kRecBytes + kRecTok + (w & 3) * 16) = v;
+    }
+    __syncwarp();
+    if (lane < in_chunk) {
+      const int st = scan_tree(recs + lane * kRecBytes, g.n_symbols);
+      if (p.status) p.status[c0 + lane] = st;
+    }
+    __syncwarp();
+
+    // ---- phases B + C, one tree at a time, whole warp cooperating
+    for (int j = 0; j < in_chunk; ++j) {
+      const uint8_t* rj = recs + j * kRecBytes;
+      const int nn = rj[kRecMeta + 0], nl = rj[kRecMeta + 1], ni = rj[kRecMeta + 2];
+      const bool bad = rj[kRecMeta + 3] != 0;
+      const int64_t row = (c0 + j) * p.ld;
+
+      if (bad) {  // malformed record: poison the row, status already written
+        const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+        for (int e = lane; e < E; e += 32) {
+          if (p.K) p.K[row + e] = qnan;
+          if (p.D) p.D[row + e] = qnan;
+          if (p.Df) { p.Df[row + e] = qnan; p.Df[p.n_cand * p.ld + row + e] = qnan; p.Df[2 * p.n_cand * p.ld + row + e] = qnan; }
+        }
+        continue;
+      }
+
+      for (int e = lane; e < e_pad; e += 32) acc[e] = 0u;
+      for (int s = lane; s < BOSOT_MAX_SYMBOLS + BOSOT_MAX_BLOCKS; s += 32) scnt[s] = 0u;
+      for (int c = lane; c < F; c += 32) avec[c] = 0.0;
+      __syncwarp();
+
+      // leaves: SUBTREES leaf classes (key = symbol) and PATHS (key = symbol * 64 + code)
+      const bool is_leaf = lane < nl;
+      const uint32_t sym = is_leaf ? rj[kRecLeafSym + lane] : 0u;
+      const uint32_t pid = is_leaf ? sym * kPathCodes + rj[kRecLeafCode + lane] : 0u;
+      const unsigned m_sym = __match_any_sync(full, is_leaf ? sym : 0x1000u + lane);
+      const unsigned m_pid = __match_any_sync(full, is_leaf ? pid : 0x10000u + lane);
+      const bool lead_sym = is_leaf && (__ffs(m_sym) - 1 == lane);
+      const bool lead_pid = is_leaf && (__ffs(m_pid) - 1 == lane);
+      uint2 r_sym = make_uint2(0u, 0u), r_pid = make_uint2(0u, 0u);
+      if (lead_sym) {
+        r_sym = __ldg(&range[hash_cap + sym]);
+        scnt[sym] = __popc(m_sym);
+        if (g.sym_block[sym] >= 0) atomicAdd(&btot[g.sym_block[sym]], (uint32_t)__popc(m_sym));
+      }
+      if (lead_pid) r_pid = __ldg(&range[hash_cap + BOSOT_MAX_SYMBOLS + pid]);
+
+      // operator nodes: SUBTREES classes through the hash table
+      const bool is_int = lane < ni;
+      const uint64_t id = is_int ? reinterpret_cast<const uint64_t*>(rj + kRecIid)[lane] : (uint64_t)lane;
+      const unsigned m_id = __match_any_sync(full, (unsigned long long)id);
+      uint2 r_int = make_uint2(0u, 0u);
+      if (is_int && (__ffs(m_id) - 1 == lane)) {
+        uint32_t s = hash_slot(id, hash_cap);
+        while (true) {
+          const unsigned long long k = __ldg(&keys[s]);
+          if (k == id) { r_int = __ldg(&range[s]); break; }
+          if (k == 0ULL) break;
+          s = (s + 1) & (uint32_t)(hash_cap - 1);
+        }
+      }
+      __syncwarp();
+
+      // candidate DIM_WISE vector from the symbol counts (optimal_transport_mappings.py:88-108)
+      for (int s = lane; s < g.n_symbols; s += 32) {
+        const int b = g.sym_block[s], c = g.sym_col[s];
+        if (b >= 0 && c >= 0) {
+          const uint32_t tot = btot[b];
+          avec[c] = tot ? (double)scnt[s] / (double)tot : 0.0;
+        }
+      }
+      if (lane < g.n_blocks) avec[g.block_null_col[lane]] = btot[lane] == 0u ? 1.0 : 0.0;
+
+      // walk the postings of every matched feature; all postings of one feature belong to
+      // distinct evaluated trees, so the read-modify-write of acc[e] needs no atomics
+      auto walk = [&](uint2 r, uint32_t cnt_a, uint32_t Ta, int shift) {
+        unsigned todo = __ballot_sync(full, r.y != 0u);
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const uint32_t beg = __shfl_sync(full, r.x, src);
+          const uint32_t len = __shfl_sync(full, r.y, src);
+          const uint32_t ca = __shfl_sync(full, cnt_a, src);
+          for (uint32_t q = lane; q < len; q += 32) {
+            const uint32_t pq = __ldg(&post[beg + q]);
+            const uint32_t e = pq & 0xffffu, cb = (pq >> 16) & 0xffu, Tb = pq >> 24;
+            acc[e] += min(ca * Tb, cb * Ta) << shift;
+          }
+          __syncwarp();
+        }
+      };
+      walk(r_sym, (uint32_t)__popc(m_sym), (uint32_t)nn, 0);
+      walk(r_int, (uint32_t)__popc(m_id), (uint32_t)nn, 0);
+      walk(r_pid, (uint32_t)__popc(m_pid), (uint32_t)nl, 16);
+      __syncwarp();
+
+      // ---- phase C: one lane per evaluated tree
+      const double rTa_sub = c_recip[nn], rTa_path = c_recip[nl];
+      for (int e = lane; e < E; e += 32) {
+        const uint32_t a = acc[e];
+        const uint32_t m_sub = a & 0xffffu, m_path = a >> 16;
+        const uint32_t tb_sub = __ldg(&e_nn[e]), tb_path = __ldg(&e_nl[e]);
+        // 2 - 2*M/(Ta*Tb); exactly 0 when the histograms coincide
+        const double d_sub = (m_sub == (uint32_t)nn * tb_sub)
+                                 ? 0.0 : fma(-2.0, ((double)m_sub * rTa_sub) * c_recip[tb_sub], 2.0);
+        const double d_path = (m_path == (uint32_t)nl * tb_path)
+                                  ? 0.0 : fma(-2.0, ((double)m_path * rTa_path) * c_recip[tb_path], 2.0);
+        double d_dim = 0.0;
+        for (int c = 0; c < F; ++c) d_dim += fabs(avec[c] - __ldg(&dimT[(size_t)c * e_pad + e]));
+        // sum_f w_f * D_f in feature_type_list order (kernel_kernel_grammar_tree.py:159-161)
+        const double d = __dadd_rn(__dadd_rn(__dmul_rn(p.w_dim, d_dim), __dmul_rn(p.w_path, d_path)),
+                                   __dmul_rn(p.w_sub, d_sub));
+        if (p.Df) {
+          p.Df[row + e] = d_dim;
+          p.Df[p.n_cand * p.ld + row + e] = d_path;
+          p.Df[2 * p.n_cand * p.ld + row + e] = d_sub;
+        }
+        if (p.D) p.D[row + e] = d;
+        if (p.K) p.K[row + e] = p.variance * exp(-1.0 * d / p.lengthscale_sq);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+static bool g_recip_ready[64] = {false};  // per device
+
+static int ensure_recip_table() {
+  int dev = 0;
+  if (int rc = cuda_check(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+  if (dev < 64 && g_recip_ready[dev]) return BOSOT_OK;
+  double h[64];
+  h[0] = 0.0;
+  for (int t = 1; t < 64; ++t) h[t] = 1.0 / (double)t;
+  if (int rc = cuda_check(cudaMemcpyToSymbol(c_recip, h, sizeof(h)), "cudaMemcpyToSymbol(c_recip)")) return rc;
+  if (dev < 64) g_recip_ready[dev] = true;
+  return BOSOT_OK;
+}
+
+int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar, const void* d_eval_blob,
+                 int n_eval, const double weights[3], double variance, double lengthscale, double* d_K, double* d_D,
+                 double* d_Df, int64_t ld, int32_t* d_status, cudaStream_t stream) {
+  if (!grammar || !d_eval_blob || !weights || n_cand < 0 || (n_cand > 0 && !d_trees))
+    return set_error(BOSOT_EINVAL, "bosot_sot_pairs: null argument");
+  if (n_eval < 1 || n_eval > BOSOT_MAX_EVAL) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: n_eval out of range");
+  if (ld < n_eval) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: ld < n_eval");
+  if (int rc = check_grammar(grammar)) return rc;
+  if (n_cand == 0) return BOSOT_OK;
+  if (int rc = ensure_recip_table()) return rc;
+
+  PairParams p;
+  p.trees = d_trees;
+  p.n_cand = n_cand;
+  p.blob = static_cast<const uint8_t*>(d_eval_blob);
+  p.L = eval_layout(n_eval);
+  p.w_dim = weights[0];
+  p.w_path = weights[1];
+  p.w_sub = weights[2];
+  p.variance = variance;
+  p.lengthscale_sq = lengthscale * lengthscale;
+  p.K = d_K;
+  p.D = d_D;
+  p.Df = d_Df;
+  p.ld = ld;
+  p.status = d_status;
+
+  const size_t smem = kPairWarps * pair_warp_smem(p.L.e_pad);
+  static bool attr_set[64] = {false};
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  if (int rc = cuda_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return rc;
+  if (!(dev < 64 && attr_set[dev])) {
+    if (int rc = cuda_check(cudaFuncSetAttribute(sot_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                            "cudaFuncSetAttribute(sot_pair_kernel)")) return rc;
+    if (dev < 64) attr_set[dev] = true;
+  }
+  if (smem > 200 * 1024) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: n_eval too large for shared memory");
+  int per_sm = 1;
+  if (int rc = cuda_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sot_pair_kernel, kPairThreads, smem),
+                          "cudaOccupancyMaxActiveBlocksPerMultiprocessor")) return rc;
+  if (per_sm < 1) per_sm = 1;
+  // grid: a whole number of waves (SMs x resident CTAs), persistent loop over 32-tree chunks
+  const int64_t want = ((n_cand + 31) / 32 + kPairWarps - 1) / kPairWarps;
+  const int64_t wave = (int64_t)sms * per_sm;
+  const int64_t grid = want < wave ? want : wave;
+  sot_pair_kernel<<<(unsigned)grid, kPairThreads, smem, stream>>>(p, *grammar);
+  return after_launch("sot_pair_kernel");
+}
+
+}  // namespace bosot
+
+extern "C" int bosot_sot_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,
+                               const void* d_eval_blob, int n_eval, const double weights[3],
+                               double variance, double lengthscale,
+                               double* d_K, double* d_D, double* d_Df, int64_t ld,
+                               int32_t* d_status, void* stream) {
+  return bosot::launch_pairs(d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale, d_K, d_D,
+                             d_Df, ld, d_status, (cudaStream_t)stream);
+}

@@ -1,0 +1,196 @@
+/*
+ * bosot_b200 -- C-ABI of the B200-native SOT kernel-kernel hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.
+ * Every entry point below replaces one step of the reference's Python hot path
+ * (boschresearch/bosot; paths relative to bosot/ in the reference tree):
+ *
+ *   flat tree encoding ........ stands in for List[BaseKernelGrammarExpression]
+ *                               (kernels/kernel_grammar/kernel_grammar.py:44-180,337-342)
+ *   bosot_featurize ........... OptimalTransportKernelKernel.internal_transform_X
+ *                               (kernels/kernel_kernel_grammar_tree.py:164-185) ->
+ *                               get_subtree_dict / get_elementary_path_dict
+ *                               (kernel_grammar.py:599-610,683-696) and
+ *                               DimWiseWeightedDistanceExtractor (optimal_transport_mappings.py:88-108)
+ *   bosot_eval_build .......... create_hash_array_mapping + feature_matrix for the
+ *                               evaluated set (kernel_kernel_grammar_tree.py:203-230),
+ *                               re-expressed as an inverted index (no global dictionary)
+ *   bosot_sot_pairs ........... wasserstein_distance / K(X, X2) / get_distance_matrix
+ *                               (kernel_kernel_grammar_tree.py:110-113,121-162) and
+ *                               manhatten_distance (utils/utils.py:168-170)
+ *   bosot_posterior_acq ....... GPR_with_posterior.predict_f as reached from
+ *                               GPModel.predictive_dist (models/gp_model.py:290-306) and the
+ *                               EI / GP-UCB formulas of BayesianOptimizerObjects.acquisition_function
+ *                               (bayesian_optimization/bayesian_optimizer_objects.py:159-168)
+ *   bosot_max_f64 ............. current_max = np.max(pred_mu_data) (same file, :165)
+ *
+ * All device pointers must belong to the current CUDA device of the calling thread.
+ * Every call is asynchronous on the given stream (a cudaStream_t passed as void*),
+ * keeps no state besides caller-owned buffers, and returns 0 on success or a negative
+ * BOSOT_E* code; it never throws or exits.  One call in flight per stream.
+ * fp64 throughout ("f64" path); the reference computes in float64 as well
+ * (kernel_kernel_grammar_tree.py:35).
+ */
+#ifndef BOSOT_B200_H
+#define BOSOT_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BOSOT_ABI_VERSION 1
+
+/* ---- flat tree encoding ("one tree = one 64-byte record") -------------------
+ * byte 0      : n = number of nodes (odd, 1..63)   => at most 32 leaves
+ * bytes 1..n  : tokens in PRE-ORDER (node, left subtree, right subtree) -- the order
+ *               in which the reference enumerates subtrees (kernel_grammar.py:469)
+ *               leaf  : symbol index 0..n_symbols-1  (< 0x80) = index of the base
+ *                       kernel in search_space.base_kernel_config_list
+ *                       (kernel_grammar_search_spaces.py:176-227)
+ *               0x80  : ADD          0x81 : MULTIPLY   (KernelGrammarOperator, kernel_grammar.py:39-41)
+ * bytes n+1.. : 0xFF padding
+ */
+#define BOSOT_TREE_BYTES 64
+#define BOSOT_MAX_NODES 63
+#define BOSOT_MAX_LEAVES 32
+#define BOSOT_MAX_INTERNAL 31
+#define BOSOT_OP_ADD 0x80
+#define BOSOT_OP_MUL 0x81
+#define BOSOT_PAD 0xFF
+
+#define BOSOT_MAX_SYMBOLS 64
+#define BOSOT_MAX_BLOCKS 16
+#define BOSOT_MAX_DIM_COLS 80
+#define BOSOT_PATH_CODES 64 /* reduced path code: 0 = empty, else 1 + 2*(len-1) + (nearest op == MULTIPLY) */
+
+/* Search-space symbol table: what DimWiseWeightedDistanceExtractor.create_dim_class_dict
+ * (optimal_transport_mappings.py:45-86) derives from generator_name/input_dimension. */
+typedef struct bosot_grammar {
+  int32_t n_symbols;                       /* B */
+  int32_t n_blocks;                        /* differentiated dimensions */
+  int32_t n_dim_cols;                      /* sum over blocks of (1 + kinds) */
+  int32_t reserved;
+  int8_t sym_block[BOSOT_MAX_SYMBOLS];     /* block of a symbol, -1 = not counted */
+  int8_t sym_col[BOSOT_MAX_SYMBOLS];       /* dim-wise column of a symbol, -1 = none */
+  int8_t block_null_col[BOSOT_MAX_BLOCKS]; /* column of NULL_i */
+} bosot_grammar;
+
+/* error codes */
+#define BOSOT_OK 0
+#define BOSOT_EINVAL (-1)  /* bad argument (null pointer, size out of range) */
+#define BOSOT_ECUDA (-2)   /* CUDA runtime error, see bosot_last_error() */
+#define BOSOT_ETREE (-3)   /* malformed tree record (only from bosot_check_status) */
+
+const char* bosot_last_error(void); /* thread-local message of the last failing call */
+int bosot_abi_version(void);
+
+/* ---- featurisation (ordered sparse histograms) ---------------------------------
+ * Per tree i (all arrays row-major, caller-allocated on the device):
+ *   n_nodes[i], n_leaves[i]
+ *   sub_n[i], sub_id[i][63], sub_cnt[i][63]   SUBTREES classes in pre-order first-occurrence
+ *                                              order; id = 64-bit canonical class id
+ *                                              (leaf: symbol+1; internal: bit 63 set)
+ *   path_n[i], path_id[i][32], path_cnt[i][32] REDUCED_ELEMENTARY_PATHS in the reference's
+ *                                              insertion order; id = symbol*64 + path code
+ *   sym_cnt[i][n_symbols]                      raw leaf counts per symbol
+ *   dimvec[i][n_dim_cols]                      DIM_WISE feature vector (fp64)
+ *   status[i]                                  0 ok, else a BOSOT_TREE_* defect code
+ * Any output pointer may be NULL (skipped) except status.
+ */
+#define BOSOT_TREE_BAD_LENGTH 1
+#define BOSOT_TREE_BAD_TOKEN 2
+#define BOSOT_TREE_BAD_SHAPE 3
+
+int bosot_featurize(const uint8_t* d_trees, int64_t n_trees, const bosot_grammar* grammar,
+                    uint8_t* d_n_nodes, uint8_t* d_n_leaves,
+                    uint8_t* d_sub_n, uint64_t* d_sub_id, uint8_t* d_sub_cnt,
+                    uint8_t* d_path_n, uint16_t* d_path_id, uint8_t* d_path_cnt,
+                    uint8_t* d_sym_cnt, double* d_dimvec, int32_t* d_status, void* stream);
+
+/* ---- evaluated-set state (inverted index over the E evaluated trees) --------------
+ * bosot_eval_state_bytes: size of the opaque device blob for E trees.
+ * bosot_eval_build: featurises the E trees and builds, inside the blob, a hash table
+ * canonical-class-id -> postings (e, count, total), direct tables for leaf symbols and
+ * reduced paths, and the transposed dim-wise matrix.  d_status: int32[E].
+ */
+#define BOSOT_MAX_EVAL 4095
+size_t bosot_eval_state_bytes(int n_eval);
+int bosot_eval_build(const uint8_t* d_trees, int n_eval, const bosot_grammar* grammar,
+                     void* d_blob, size_t blob_bytes, int32_t* d_status, void* stream);
+
+/* ---- SOT pair kernel ------------------------------------------------------------
+ * For every candidate tree c (row) and evaluated tree e (column):
+ *   Df[f][c][e] = L1 distance of the f-th feature histograms, f = 0 DIM_WISE, 1 PATHS, 2 SUBTREES
+ *   D[c][e]     = sum_f weights[f] * Df[f][c][e]        (weights = alpha_f / sum(alpha), 0 = feature off)
+ *   K[c][e]     = variance * exp(-D / lengthscale^2)
+ * Outputs are [n_cand][ld] fp64 with leading dimension ld >= n_eval (Df: 3 planes of
+ * n_cand*ld); any of d_K / d_D / d_Df may be NULL.  d_status: int32[n_cand] tree defects.
+ */
+int bosot_sot_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,
+                    const void* d_eval_blob, int n_eval, const double weights[3],
+                    double variance, double lengthscale,
+                    double* d_K, double* d_D, double* d_Df, int64_t ld,
+                    int32_t* d_status, void* stream);
+
+/* ---- GP posterior + acquisition -----------------------------------------------------
+ * Inputs: K*[n_cand][ld] (rows = candidates), LinvT[n_eval][ldl] = transpose of the
+ * inverse of the lower Cholesky factor of K_EE + noise*I (so column i of LinvT is row i
+ * of L^-1; row-major, upper triangular; ldl >= n_eval a multiple of 8, columns >= n_eval
+ * zero, base 16-byte aligned), beta[n_eval] = (K_EE + noise*I)^-1 (y - c).
+ *   mu    = K* . beta + mean_c
+ *   var   = variance - || L^-1 k* ||^2          (K_diag == variance: d(x,x) = 0 exactly)
+ *   sigma = sqrt(var)                           (NaN if var < 0, as in the reference)
+ *   acq   = EI:  d*Phi(d/sigma) + sigma*phi(d/sigma),  d = mu - *d_current_max - xi
+ *           UCB: mu + sqrt(ucb_beta)*sigma
+ * d_current_max is a device scalar (ignored for UCB / NONE).  Any of mu/sigma/acq may be NULL.
+ */
+#define BOSOT_ACQ_NONE 0
+#define BOSOT_ACQ_EI 1
+#define BOSOT_ACQ_UCB 2
+
+int bosot_posterior_acq(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval,
+                        const double* d_LinvT, int ldl, const double* d_beta, double mean_c, double variance,
+                        int acq_kind, const double* d_current_max, double xi, double ucb_beta,
+                        double* d_mu, double* d_sigma, double* d_acq, void* stream);
+
+/* max of n doubles into a device scalar (NaNs ignored like fmax) */
+int bosot_max_f64(const double* d_x, int64_t n, double* d_out, void* stream);
+
+/* ---- host-buffer convenience (the end-to-end call) --------------------------------------
+ * Candidates in (preferably pinned) host memory -> acquisition values in host memory.
+ * Copies h_trees to d_trees_scratch, runs pairs + posterior, copies acq (and mu/sigma when
+ * non-NULL) back, all on `stream`; the caller synchronises the stream.
+ * d_work: device scratch of bosot_acquire_work_bytes(n_cand, n_eval) bytes.
+ */
+size_t bosot_acquire_work_bytes(int64_t n_cand, int n_eval);
+int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const bosot_grammar* grammar,
+                       const void* d_eval_blob, int n_eval, const double weights[3],
+                       double variance, double lengthscale,
+                       const double* d_LinvT, int ldl, const double* d_beta, double mean_c,
+                       int acq_kind, const double* d_current_max, double xi, double ucb_beta,
+                       void* d_work, size_t work_bytes,
+                       double* h_mu, double* h_sigma, double* h_acq, void* stream);
+
+/* same, candidates already on the device, outputs on the device */
+int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,
+                         const void* d_eval_blob, int n_eval, const double weights[3],
+                         double variance, double lengthscale,
+                         const double* d_LinvT, int ldl, const double* d_beta, double mean_c,
+                         int acq_kind, const double* d_current_max, double xi, double ucb_beta,
+                         void* d_work, size_t work_bytes,
+                         double* d_mu, double* d_sigma, double* d_acq, void* stream);
+
+/* ---- measurement helpers -----------------------------------------------------------------
+ * bosot_fp64_fma_probe: runs `iters` dependent-chain-free DFMA per thread on a full grid so
+ * bench.py can measure this GPU's fp64 FMA ceiling (the secondary roofline of the posterior).
+ * bosot_kernel_launch_count: number of kernels this library has launched in this process. */
+int bosot_fp64_fma_probe(double* d_out, int n_blocks, int n_threads, int iters, void* stream);
+int64_t bosot_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOSOT_B200_H */
