@@ -32,7 +32,9 @@ featurize_kernel(const uint8_t* __restrict__ trees, int64_t n_trees, bosot_gramm
   for (int w = threadIdx.x; w < in_block * (kTreeBytes / 16); w += kFeatThreads) {
     const int t = w / (kTreeBytes / 16), q = w % (kTreeBytes / 16);
     const uint4 v = reinterpret_cast<const uint4*>(trees + (base + t) * kTreeBytes)[q];
-    *reinterpret_cast<uint4*>(smem + t * kRecBytes + kRecTok + q * 16) = v;
+    uint2* dst = reinterpret_cast<uint2*>(smem + t * kRecBytes + kRecTok + q * 16);  // records are 8-byte aligned
+    dst[0] = make_uint2(v.x, v.y);
+    dst[1] = make_uint2(v.z, v.w);
   }
   __syncthreads();
   if ((int)threadIdx.x >= in_block) return;

@@ -82,7 +82,9 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     __syncwarp();
     for (int w = lane; w < in_chunk * 4; w += 32) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.trees + c0 * kTreeBytes) + w);
-      *reinterpret_cast<uint4*>(recs + (w >> 2) * kRecBytes + kRecTok + (w & 3) * 16) = v;
+      uint2* dst = reinterpret_cast<uint2*>(recs + (w >> 2) * kRecBytes + kRecTok + (w & 3) * 16);  // 8-byte aligned
+      dst[0] = make_uint2(v.x, v.y);
+      dst[1] = make_uint2(v.z, v.w);
     }
     __syncwarp();
     if (lane < in_chunk) {
@@ -184,11 +186,11 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
         const uint32_t a = acc[e];
         const uint32_t m_sub = a & 0xffffu, m_path = a >> 16;
         const uint32_t tb_sub = __ldg(&e_nn[e]), tb_path = __ldg(&e_nl[e]);
-        // 2 - 2*M/(Ta*Tb); exactly 0 when the histograms coincide
+        // 2 - 2*M/(Ta*Tb); exactly 0 when the histograms coincide; (1/Ta)*(1/Tb) first keeps D(a,b) == D(b,a) bitwise
         const double d_sub = (m_sub == (uint32_t)nn * tb_sub)
-                                 ? 0.0 : fma(-2.0, ((double)m_sub * rTa_sub) * c_recip[tb_sub], 2.0);
+                                 ? 0.0 : fma(-2.0, (double)m_sub * (rTa_sub * c_recip[tb_sub]), 2.0);
         const double d_path = (m_path == (uint32_t)nl * tb_path)
-                                  ? 0.0 : fma(-2.0, ((double)m_path * rTa_path) * c_recip[tb_path], 2.0);
+                                  ? 0.0 : fma(-2.0, (double)m_path * (rTa_path * c_recip[tb_path]), 2.0);
         double d_dim = 0.0;
         for (int c = 0; c < F; ++c) d_dim += fabs(avec[c] - __ldg(&dimT[(size_t)c * e_pad + e]));
         // sum_f w_f * D_f in feature_type_list order (kernel_kernel_grammar_tree.py:159-161)
