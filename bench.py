@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Headline benchmark of the SOT kernel-kernel hot path (BASELINE.json: "SOT OT-pairs/sec and EI
+candidates/sec at 1/2/4/8 B200 vs host-CPU ref").
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+
+One "step" = one pass of the hot path over the whole candidate pool: flat trees -> in-SM
+featurisation -> SOT pair distances against the evaluated set -> Gram -> GP posterior mean/variance
+-> Expected Improvement, then ONE NCCL all-gather of the EI vector when the pool is row-sharded
+over several GPUs (strong scaling: the pool is fixed, BASELINE.json config 5).
+
+Workload (config.workload): "c5_stress_1M_x_200" = 1,000,000 random grammar trees (depth <= 5,
+CKSHighDimSearchSpace d=5) x 200 evaluated trees, hyper-parameters H1 of SURVEY.md 8d.  The C4
+headline shape (10,000 candidates x 50 evaluated) is measured in the same run and reported under
+"c4_10k_x_50".  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GEN, DIM = "CKSHighDimSearchSpace", 5
+POOL, N_EVAL = 1_000_000, 200
+C4_POOL, C4_EVAL = 10_000, 50
+HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback, used only when MEASURED_PEAKS.json is absent
+# "trained-like" hyper-parameters H1 of SURVEY.md 8d
+H1 = dict(alphas=(0.2, 0.7, 0.4), lengthscale=0.8, variance=1.3, noise_variance=1e-3, mean_c=-0.5)
+
+
+def algorithmic_bytes_per_pair(n_cand: int, n_eval: int) -> float:
+    """one fp64 Gram entry written, each 64-byte flat tree read once."""
+    return 8.0 + 64.0 / n_eval + 64.0 / n_cand
+
+
+class ClockSampler:
+    """nvidia-smi SM clocks + throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=10)
+
+    def summary(self) -> dict:
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+def measured_peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return dict(json.load(f), source="measured")
+    return dict(hbm_gbs=HBM_FALLBACK_GBS, source="fallback")
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank: int) -> None:
+    if rank != 0:
+        return
+    from bosot_b200.encoding import Grammar, random_stress_trees
+    from oracle import cpu_baseline
+
+    gram = Grammar.get(GEN, DIM)
+    ev = random_stress_trees(N_EVAL, gram, seed=77)
+    y = np.random.default_rng(4).standard_normal(N_EVAL)
+    cores = os.cpu_count() or 1
+    sample = 100 * cores  # one reference-shaped call (population 100) per host core per step
+    times = []
+    for s in range(args.warmup + args.steps):
+        ca = random_stress_trees(sample, gram, seed=1234 + s)
+        r = cpu_baseline.run(ev, ca, y, H1, GEN, DIM, chunk=100, n_procs=cores)
+        if s >= args.warmup:
+            times.append(r["seconds"])
+    sec = float(np.mean(times))
+    value = sample * N_EVAL / sec
+    line = dict(
+        impl="reference", metric="sot_ot_pairs_per_sec", value=value, unit="pairs/s", n_gpus=args.gpus, steps=args.steps,
+        warmup=args.warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64",
+        data="synthetic",
+        config=dict(workload="c5_stress_1M_x_200", n_eval=N_EVAL, generator=GEN, input_dimension=DIM, hyper="H1",
+                    sample="%d candidates x %d evaluated per step (bounded sample of the 1M pool)" % (sample, N_EVAL)),
+        ei_candidates_per_sec=sample / sec,
+        cpu_baseline=dict(value=value, unit="pairs/s", cores=cores, kind="port",
+                          sample="%d candidates x %d evaluated per step, %d worker processes x calls of 100 candidates; "
+                                 "K_diag taken as variance" % (sample, N_EVAL, cores)),
+        e2e=dict(value=value, unit="pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+        gpu_launches=0,
+    )
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ our arm
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pool", type=int, default=POOL)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the cpu_baseline sample (0 = 100 per core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from bosot_b200 import _lib, sot
+    from bosot_b200.encoding import Grammar, random_stress_trees
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; the hot path has no CPU fallback")
+    _lib.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.warmup < 3:
+        args.warmup = 3  # timing hygiene: at least 3 warm-up steps
+
+    gram = Grammar.get(GEN, DIM)
+    hyp = argparse.Namespace(**H1)
+    w = np.asarray(hyp.alphas, dtype=np.float64) / np.sum(np.asarray(hyp.alphas, dtype=np.float64))
+    pool = args.pool
+    lo, hi = rank * pool // world, (rank + 1) * pool // world
+    n_local = hi - lo
+
+    # synthetic inputs: evaluated set replicated, candidate shard per rank
+    ev_np = random_stress_trees(N_EVAL, gram, seed=77)
+    y = np.random.default_rng(4).standard_normal(N_EVAL)
+    ca_np = random_stress_trees(n_local, gram, seed=1234 + rank)
+    d_ev = sot.as_device_trees(ev_np, dev)
+    d_ca = sot.as_device_trees(ca_np, dev)
+    h_ca = torch.from_numpy(ca_np).pin_memory()
+    eng = sot.AcquisitionEngine(d_ev, torch.from_numpy(y), gram, w, hyp.variance, hyp.lengthscale, hyp.noise_variance, hyp.mean_c)
+
+    mu = torch.empty(n_local, dtype=torch.float64, device=dev)
+    sigma = torch.empty_like(mu)
+    ei_local = torch.empty_like(mu)
+    ei_full = torch.empty(pool, dtype=torch.float64, device=dev) if world > 1 else ei_local
+    h_ei = torch.empty(pool, dtype=torch.float64).pin_memory()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier(collective=True):
+        if world > 1 and collective:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_device():
+        eng.acquire_device(d_ca, out=(mu, sigma, ei_local))
+        if world > 1:
+            dist.all_gather_into_tensor(ei_full, ei_local)
+
+    def step_e2e():
+        # N = 1: host flat trees -> device -> EI -> host through the host-buffer entry point
+        eng.acquire_host(h_ca, h_ei, sync=True)
+
+    d_stage = torch.empty_like(d_ca)
+
+    def step_e2e_multi():
+        # N > 1: pinned H2D of the shard, kernels, all-gather on the device, pinned D2H of the full EI vector
+        d_stage.copy_(h_ca, non_blocking=True)
+        eng.acquire_device(d_stage, out=(mu, sigma, ei_local))
+        dist.all_gather_into_tensor(ei_full, ei_local)
+        h_ei.copy_(ei_full, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+
+    def timed(fn, steps, warmup, flush_l2=True, collective=True):
+        for _ in range(warmup):
+            fn()
+        barrier(collective)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in evs:
+            if flush_l2:
+                flush.zero_()  # untimed: evicts the pool / Gram panel from L2 between timed steps
+            a.record()
+            fn()
+            b.record()
+        barrier(collective)
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1 and collective:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t) / steps
+
+    launches0 = _lib.launch_count()
+    with ClockSampler(local_rank) as clocks:
+        ms_step = timed(step_device, args.steps, args.warmup)
+    launches = (_lib.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
+
+    # end to end through the host-buffer API (H2D trees, kernels, all-gather, D2H EI inside the timed region)
+    ms_e2e = timed(step_e2e_multi if world > 1 else step_e2e, args.steps, args.warmup)
+
+    # per-kernel durations (CUDA events on the launching stream) for the roofline object
+    Kbuf = torch.empty((n_local, N_EVAL), dtype=torch.float64, device=dev)
+    status = torch.empty(n_local, dtype=torch.int32, device=dev)
+    import ctypes as C
+
+    lib = _lib.load()
+    wd = (C.c_double * 3)(*[float(x) for x in w])
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def k_pairs():
+        _lib.check(lib.bosot_sot_pairs(d_ca.data_ptr(), n_local, C.byref(gram.c_struct), eng.state.blob.data_ptr(), N_EVAL, wd,
+                                       hyp.variance, hyp.lengthscale, Kbuf.data_ptr(), None, None, N_EVAL, status.data_ptr(), stream))
+
+    def k_post():
+        _lib.check(lib.bosot_posterior_acq(Kbuf.data_ptr(), n_local, N_EVAL, N_EVAL, eng.LinvT.data_ptr(), eng.LinvT.shape[1],
+                                           eng.beta.data_ptr(), hyp.mean_c, hyp.variance, _lib.ACQ_EI, eng.current_max.data_ptr(),
+                                           0.01, 3.0, mu.data_ptr(), sigma.data_ptr(), ei_local.data_ptr(), stream))
+
+    ms_pairs = timed(k_pairs, args.steps, 3, collective=False)
+    ms_post = timed(k_post, args.steps, 3, collective=False)
+
+    # fp64 FMA ceiling of this GPU (secondary roofline of the posterior kernel)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    probe_out = torch.empty(sms * 8 * 256, dtype=torch.float64, device=dev)
+    iters = 4096
+
+    def k_probe():
+        _lib.check(lib.bosot_fp64_fma_probe(probe_out.data_ptr(), sms * 8, 256, iters, stream))
+
+    ms_probe = timed(k_probe, 5, 2, flush_l2=False, collective=False)
+    fp64_tflops = 2.0 * sms * 8 * 256 * 8 * iters / (ms_probe * 1e-3) / 1e12
+
+    # C4 headline shape: 10k candidates x 50 evaluated (one GPU's worth; measured on every rank, reported from rank 0)
+    c4 = {}
+    if rank == 0:
+        ev4 = random_stress_trees(C4_EVAL, gram, seed=78)
+        ca4 = random_stress_trees(C4_POOL, gram, seed=4321)
+        y4 = np.random.default_rng(5).standard_normal(C4_EVAL)
+        eng4 = sot.AcquisitionEngine(sot.as_device_trees(ev4, dev), torch.from_numpy(y4), gram, w, hyp.variance, hyp.lengthscale,
+                                     hyp.noise_variance, hyp.mean_c)
+        d4 = sot.as_device_trees(ca4, dev)
+        h4 = torch.from_numpy(ca4).pin_memory()
+        h4_ei = torch.empty(C4_POOL, dtype=torch.float64).pin_memory()
+        o4 = tuple(torch.empty(C4_POOL, dtype=torch.float64, device=dev) for _ in range(3))
+        ms4 = timed(lambda: eng4.acquire_device(d4, out=o4), 20, 5, collective=False)
+        ms4_e2e = timed(lambda: eng4.acquire_host(h4, h4_ei, sync=True), 20, 5, collective=False)
+        c4 = dict(workload="c4_airfoil_10k_x_50", ms_per_step=ms4, pairs_per_s=C4_POOL * C4_EVAL / (ms4 * 1e-3),
+                  ei_candidates_per_s=C4_POOL / (ms4 * 1e-3), e2e_ms=ms4_e2e, e2e_pairs_per_s=C4_POOL * C4_EVAL / (ms4_e2e * 1e-3),
+                  e2e_ei_candidates_per_s=C4_POOL / (ms4_e2e * 1e-3))
+
+    peaks = measured_peaks()
+    pairs = pool * N_EVAL
+    value = pairs / (ms_step * 1e-3)
+    e2e_value = pairs / (ms_e2e * 1e-3)
+    b_pair = algorithmic_bytes_per_pair(n_local, N_EVAL)
+    dominant = "sot_pair_kernel" if ms_pairs >= ms_post else "posterior_kernel"
+    if dominant == "sot_pair_kernel":
+        alg_bytes = b_pair * n_local * N_EVAL
+        dur = ms_pairs
+    else:  # posterior: K* panel read once, mu/sigma/EI written
+        alg_bytes = (8.0 * N_EVAL + 24.0) * n_local
+        dur = ms_post
+    achieved = alg_bytes / (dur * 1e-3) / 1e9
+    post_flops = n_local * (float(N_EVAL) * (N_EVAL + 1) + 4.0 * N_EVAL)  # triangular product + mean + norm
+    roofline = dict(
+        bound="hbm", kernel=dominant, achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
+        traffic=None, peak_source=peaks["source"],
+        algorithmic_bytes_per_launch=alg_bytes, kernel_ms=dur,
+        kernels_ms=dict(sot_pair_kernel=ms_pairs, posterior_kernel=ms_post),
+        note="fp64 issue, not HBM, is the practical ceiling of both kernels (DESIGN.md); secondary ceiling below",
+        fp64=dict(measured_dfma_tflops=fp64_tflops, posterior_tflops=post_flops / (ms_post * 1e-3) / 1e12,
+                  posterior_frac_of_dfma_peak=post_flops / (ms_post * 1e-3) / 1e12 / fp64_tflops),
+    )
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline
+
+        cores = os.cpu_count() or 1
+        sample = args.cpu_sample or 100 * cores
+        r = cpu_baseline.run(ev_np, ca_np[:sample], y, H1, GEN, DIM, chunk=100, n_procs=cores)
+        # the sample doubles as a parity check of this very run
+        got = ei_local[:sample].cpu().numpy()
+        ok = bool(np.allclose(got, r["acq"], rtol=1e-6, atol=1e-12))
+        cpu = dict(value=r["pairs_per_s"], unit="pairs/s", cores=r["cores"], kind="port",
+                   sample="first %d candidates of the pool x %d evaluated in %.1f s: %d worker processes, calls of 100 "
+                          "candidates; K_diag taken as variance" % (sample, N_EVAL, r["seconds"], r["cores"]),
+                   ei_candidates_per_sec=r["cand_per_s"], gpu_matches_cpu_on_sample=ok)
+
+    if rank == 0:
+        line = dict(
+            metric="sot_ot_pairs_per_sec", value=value, unit="pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
+            config=dict(workload="c5_stress_1M_x_200", pool=pool, n_eval=N_EVAL, generator=GEN, input_dimension=DIM, hyper="H1",
+                        sharding="candidate row blocks, %d per GPU" % n_local, collective="all_gather(EI) x1" if world > 1 else "none",
+                        l2="flushed between timed steps (512 MB memset, untimed); working set also exceeds L2"),
+            ei_candidates_per_sec=pool / (ms_step * 1e-3),
+            clocks=clocks.summary(),
+            e2e=dict(value=e2e_value, unit="pairs/s", ms_per_step=ms_e2e, ei_candidates_per_sec=pool / (ms_e2e * 1e-3),
+                     h2d_bytes_per_step=pool * 64, d2h_bytes_per_step=pool * 8 * world,
+                     api="AcquisitionEngine.acquire_host (C-ABI bosot_acquire_host)" if world == 1 else
+                         "pinned H2D + AcquisitionEngine.acquire_device + all_gather + pinned D2H"),
+            gpu_launches=launches * world,
+            roofline=roofline,
+            cpu_baseline=cpu,
+            c4_10k_x_50=c4,
+        )
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
