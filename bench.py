@@ -249,7 +249,7 @@ def main() -> None:
                                        hyp.variance, hyp.lengthscale, Kbuf.data_ptr(), None, None, N_EVAL, status.data_ptr(), stream))
 
     def k_post():
-        _lib.check(lib.bosot_posterior_acq(Kbuf.data_ptr(), n_local, N_EVAL, N_EVAL, eng.LinvT.data_ptr(), eng.LinvT.shape[1],
+        _lib.check(lib.bosot_posterior_acq(Kbuf.data_ptr(), n_local, N_EVAL, N_EVAL, eng.Linv.data_ptr(), eng.Linv.shape[1],
                                            eng.beta.data_ptr(), hyp.mean_c, hyp.variance, _lib.ACQ_EI, eng.current_max.data_ptr(),
                                            0.01, 3.0, mu.data_ptr(), sigma.data_ptr(), ei_local.data_ptr(), stream))
 
@@ -266,6 +266,12 @@ def main() -> None:
 
     ms_probe = timed(k_probe, 5, 2, flush_l2=False, collective=False)
     fp64_tflops = 2.0 * sms * 8 * 256 * 8 * iters / (ms_probe * 1e-3) / 1e12
+
+    def k_probe_mma():
+        _lib.check(lib.bosot_fp64_mma_probe(probe_out.data_ptr(), sms * 8, 256, iters, stream))
+
+    ms_probe_mma = timed(k_probe_mma, 5, 2, flush_l2=False, collective=False)
+    dmma_tflops = 2.0 * sms * 8 * (256 // 32) * 8 * 256 * iters / (ms_probe_mma * 1e-3) / 1e12
 
     # C4 headline shape: 10k candidates x 50 evaluated (one GPU's worth; measured on every rank, reported from rank 0)
     c4 = {}
@@ -305,8 +311,9 @@ def main() -> None:
         algorithmic_bytes_per_launch=alg_bytes, kernel_ms=dur,
         kernels_ms=dict(sot_pair_kernel=ms_pairs, posterior_kernel=ms_post),
         note="fp64 issue, not HBM, is the practical ceiling of both kernels (DESIGN.md); secondary ceiling below",
-        fp64=dict(measured_dfma_tflops=fp64_tflops, posterior_tflops=post_flops / (ms_post * 1e-3) / 1e12,
-                  posterior_frac_of_dfma_peak=post_flops / (ms_post * 1e-3) / 1e12 / fp64_tflops),
+        fp64=dict(measured_dfma_tflops=fp64_tflops, measured_dmma_tflops=dmma_tflops,
+                  posterior_tflops=post_flops / (ms_post * 1e-3) / 1e12,
+                  posterior_frac_of_dmma_peak=post_flops / (ms_post * 1e-3) / 1e12 / dmma_tflops),
     )
 
     cpu = None

@@ -68,6 +68,7 @@ SIGNATURES = {
          _P, C.c_size_t, _P, _P, _P, _P],
     ),
     "bosot_fp64_fma_probe": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
+    "bosot_fp64_mma_probe": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "bosot_kernel_launch_count": (C.c_int64, []),
 }
 

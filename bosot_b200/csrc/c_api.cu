@@ -44,7 +44,7 @@ int check_grammar(const bosot_grammar* g) {
 int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar, const void* d_eval_blob,
                  int n_eval, const double weights[3], double variance, double lengthscale, double* d_K, double* d_D,
                  double* d_Df, int64_t ld, int32_t* d_status, cudaStream_t stream);
-int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval, const double* d_LinvT, int ldl,
+int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval, const double* d_Linv, int ldl,
                      const double* d_beta, double mean_c, double variance, int acq_kind, const double* d_current_max,
                      double xi, double ucb_beta, double* d_mu, double* d_sigma, double* d_acq, cudaStream_t stream);
 
@@ -76,10 +76,10 @@ extern "C" int bosot_abi_version(void) { return BOSOT_ABI_VERSION; }
 extern "C" int64_t bosot_kernel_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int bosot_posterior_acq(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval,
-                                   const double* d_LinvT, int ldl, const double* d_beta, double mean_c, double variance,
+                                   const double* d_Linv, int ldl, const double* d_beta, double mean_c, double variance,
                                    int acq_kind, const double* d_current_max, double xi, double ucb_beta,
                                    double* d_mu, double* d_sigma, double* d_acq, void* stream) {
-  return launch_posterior(d_Kstar, n_cand, ld, n_eval, d_LinvT, ldl, d_beta, mean_c, variance, acq_kind, d_current_max,
+  return launch_posterior(d_Kstar, n_cand, ld, n_eval, d_Linv, ldl, d_beta, mean_c, variance, acq_kind, d_current_max,
                           xi, ucb_beta, d_mu, d_sigma, d_acq, (cudaStream_t)stream);
 }
 
@@ -91,7 +91,7 @@ extern "C" size_t bosot_acquire_work_bytes(int64_t n_cand, int n_eval) {
 extern "C" int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,
                                     const void* d_eval_blob, int n_eval, const double weights[3],
                                     double variance, double lengthscale,
-                                    const double* d_LinvT, int ldl, const double* d_beta, double mean_c,
+                                    const double* d_Linv, int ldl, const double* d_beta, double mean_c,
                                     int acq_kind, const double* d_current_max, double xi, double ucb_beta,
                                     void* d_work, size_t work_bytes,
                                     double* d_mu, double* d_sigma, double* d_acq, void* stream) {
@@ -105,14 +105,14 @@ extern "C" int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, cons
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = launch_pairs(d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale, K, nullptr,
                             nullptr, W.ld, status, st)) return rc;
-  return launch_posterior(K, n_cand, W.ld, n_eval, d_LinvT, ldl, d_beta, mean_c, variance, acq_kind, d_current_max, xi,
+  return launch_posterior(K, n_cand, W.ld, n_eval, d_Linv, ldl, d_beta, mean_c, variance, acq_kind, d_current_max, xi,
                           ucb_beta, d_mu, d_sigma, d_acq, st);
 }
 
 extern "C" int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const bosot_grammar* grammar,
                                   const void* d_eval_blob, int n_eval, const double weights[3],
                                   double variance, double lengthscale,
-                                  const double* d_LinvT, int ldl, const double* d_beta, double mean_c,
+                                  const double* d_Linv, int ldl, const double* d_beta, double mean_c,
                                   int acq_kind, const double* d_current_max, double xi, double ucb_beta,
                                   void* d_work, size_t work_bytes,
                                   double* h_mu, double* h_sigma, double* h_acq, void* stream) {
@@ -128,7 +128,7 @@ extern "C" int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const 
   double* d_sigma = reinterpret_cast<double*>(w + W.off_sigma);
   double* d_acq = reinterpret_cast<double*>(w + W.off_acq);
   if (int rc = cuda_check(cudaMemcpyAsync(d_trees, h_trees, (size_t)n_cand * kTreeBytes, cudaMemcpyHostToDevice, st), "H2D trees")) return rc;
-  if (int rc = bosot_acquire_device(d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale, d_LinvT,
+  if (int rc = bosot_acquire_device(d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale, d_Linv,
                                     ldl, d_beta, mean_c, acq_kind, d_current_max, xi, ucb_beta, d_work, work_bytes,
                                     h_mu ? d_mu : nullptr, h_sigma ? d_sigma : nullptr, h_acq ? d_acq : nullptr, stream)) return rc;
   const size_t nb = sizeof(double) * (size_t)n_cand;

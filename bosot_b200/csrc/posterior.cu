@@ -13,8 +13,11 @@
 //
 // Shape of the work: V[i][c] = sum_{j<=i} Linv[i][j] * K*[c][j]  -- a lower-triangular E x E
 // matrix times an E x N panel in fp64, reduced on the fly to sum_i V[i][c]^2; V is never stored.
-// CTA = 64 candidates (K* tile staged in shared memory), 8 warps split the row blocks of L^-1;
-// each lane keeps an 8-row x 2-candidate register tile of DFMA accumulators.
+// This IS a dense fp64 contraction, so it runs on the fp64 tensor path: mma.sync m8n8k4 (DMMA;
+// tcgen05 has no fp64 kind).  CTA = 64 candidates (K* tile staged in shared memory, B operand),
+// L^-1 streamed from L2 exactly once per CTA (A operand): the 8 warps pull 16-row blocks of L^-1
+// from a shared work counter, largest block first, so the triangular cost profile balances itself;
+// partial sums go to a per-block slot and are added in block order => bitwise reproducible.
 #include "sot_common.cuh"
 #include "launch.cuh"
 
@@ -22,16 +25,17 @@ namespace bosot {
 
 constexpr int kPostThreads = 256;
 constexpr int kPostWarps = kPostThreads / 32;
-constexpr int kPostCand = 64;  // candidates per CTA tile
-constexpr int kRowBlk = 8;     // rows of L^-1 per register tile
+constexpr int kPostCand = 64;            // candidates per CTA tile = 8 n-blocks of 8
+constexpr int kNB = kPostCand / 8;
+constexpr int kRowBlk = 16;              // rows of L^-1 per work unit = 2 m-blocks of 8
 
 struct PostParams {
   const double* Kstar;
   int64_t n_cand;
   int64_t ld;
   int E;
-  int ldl;  // leading dimension of LinvT (multiple of kRowBlk, zero padded)
-  const double* LinvT;
+  int ldl;  // leading dimension (and padded row count) of Linv: multiple of 16, zero padded
+  const double* Linv;
   const double* beta;
   double mean_c, variance;
   int acq_kind;
@@ -42,30 +46,45 @@ struct PostParams {
   double* acq;
 };
 
-__host__ __device__ inline int post_tile_ld(int E) { return E | 1; }  // odd stride: conflict-free row reads
+// K* tile row stride (doubles): == 4 or 12 (mod 16) so that the B-fragment read
+// Ks[8*nb + lane/4][4*ks + lane%4] hits 16 distinct 8-byte banks per half warp
+__host__ __device__ inline int post_tile_ld(int E) {
+  const int e4 = (E + 3) & ~3;
+  return (e4 % 8 == 4) ? e4 : e4 + 4;
+}
 
 __device__ __forceinline__ double norm_cdf(double z) { return 0.5 * erfc(-z * 0.70710678118654752440); }
 __device__ __forceinline__ double norm_pdf(double z) { return 0.39894228040143267794 * exp(-0.5 * z * z); }
 
-__global__ void __launch_bounds__(kPostThreads)
+// D(8x8) += A(8x4, row) * B(4x8, col), fp64.  Lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kPostThreads, 2)
 posterior_kernel(PostParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int E = p.E;
   const int tld = post_tile_ld(E);
-  double* Ks = reinterpret_cast<double*>(smem);            // [64][tld]
-  double* red = Ks + (size_t)kPostCand * tld;              // [kPostWarps][64] partial sums of v^2
-  double* mus = red + kPostWarps * kPostCand;              // [64]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n_rb = (E + kRowBlk - 1) / kRowBlk;
+  const int n_blk = (E + kRowBlk - 1) / kRowBlk;
+  const int ks_max = (E + 3) >> 2;                            // k-steps that hold real columns
+  double* Ks = reinterpret_cast<double*>(smem);              // [64][tld]
+  double* red = Ks + (size_t)kPostCand * tld;                // [n_blk][64] per-block sums of v^2
+  double* mus = red + (size_t)n_blk * kPostCand;             // [64]
+  int* work = reinterpret_cast<int*>(mus + kPostCand);       // shared work counter
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
 
   for (int64_t tile = blockIdx.x; tile * kPostCand < p.n_cand; tile += gridDim.x) {
     const int64_t c0 = tile * kPostCand;
     const int in_tile = (int)min((int64_t)kPostCand, p.n_cand - c0);
     __syncthreads();
-    // stage the K* tile (rows = candidates); rows beyond the tile are zero
-    for (int x = threadIdx.x; x < kPostCand * E; x += kPostThreads) {
-      const int c = x / E, j = x % E;
-      Ks[c * tld + j] = c < in_tile ? __ldg(&p.Kstar[(c0 + c) * p.ld + j]) : 0.0;
+    if (threadIdx.x == 0) *work = 0;
+    // stage the K* tile (rows = candidates); rows beyond the tile and columns >= E are zero
+    for (int x = threadIdx.x; x < kPostCand * tld; x += kPostThreads) {
+      const int c = x / tld, j = x - c * tld;
+      Ks[x] = (c < in_tile && j < E) ? __ldg(&p.Kstar[(c0 + c) * p.ld + j]) : 0.0;
     }
     __syncthreads();
 
@@ -79,58 +98,78 @@ posterior_kernel(PostParams p) {
       if (q == 0) mus[c] = s + p.mean_c;
     }
 
-    // variance: row blocks of L^-1 dealt to the warps in snake order (cost grows with the row index)
-    double ss0 = 0.0, ss1 = 0.0;
-    const double* k0 = Ks + lane * tld;
-    const double* k1 = Ks + (lane + 32) * tld;
-    for (int round = 0; round * kPostWarps < n_rb; ++round) {
-      const int rb = round * kPostWarps + ((round & 1) ? (kPostWarps - 1 - warp) : warp);
-      if (rb >= n_rb) continue;
-      const int i0 = rb * kRowBlk;
-      const int jend = min(E, i0 + kRowBlk);
-      double a0[kRowBlk], a1[kRowBlk];
+    // variance: pull 16-row blocks of L^-1, largest first
+    while (true) {
+      int m = 0;
+      if (lane == 0) m = atomicAdd(work, 1);
+      m = n_blk - 1 - __shfl_sync(0xffffffffu, m, 0);
+      if (m < 0) break;
+      const int i0 = m * kRowBlk;
+      const int nks = min(i0 / 4 + 4, ks_max);     // columns j < i0 + 16 (and < E4)
+      const int nks_up = min(i0 / 4 + 2, ks_max);  // upper 8 rows only reach j < i0 + 8
+      const bool lower_live = i0 + 8 < E;          // lower 8 rows may be pure padding in the last block
+      double up[kNB][2], lo[kNB][2];
 #pragma unroll
-      for (int r = 0; r < kRowBlk; ++r) { a0[r] = 0.0; a1[r] = 0.0; }
-      const double* lt = p.LinvT + i0;
-      for (int j = 0; j < jend; ++j) {
-        const double x0 = k0[j], x1 = k1[j];
-        const double2* l2 = reinterpret_cast<const double2*>(lt + (size_t)j * p.ldl);
+      for (int nb = 0; nb < kNB; ++nb) { up[nb][0] = up[nb][1] = 0.0; lo[nb][0] = lo[nb][1] = 0.0; }
+      const double* a_up = p.Linv + (size_t)(i0 + g) * p.ldl + t;
+      const double* a_lo = a_up + (size_t)8 * p.ldl;
+      const double* bp = Ks + g * tld + t;
+      double an_up = __ldg(a_up), an_lo = lower_live ? __ldg(a_lo) : 0.0;
+      for (int ks = 0; ks < nks; ++ks) {
+        const double au = an_up, al = an_lo;
+        if (ks + 1 < nks) {  // prefetch the next A fragments (L2 latency) behind this step's 16 DMMAs
+          an_up = (ks + 1 < nks_up) ? __ldg(a_up + 4 * (ks + 1)) : 0.0;
+          an_lo = lower_live ? __ldg(a_lo + 4 * (ks + 1)) : 0.0;
+        }
+        double b[kNB];
 #pragma unroll
-        for (int r = 0; r < kRowBlk / 2; ++r) {
-          const double2 l = __ldg(&l2[r]);
-          a0[2 * r] = fma(l.x, x0, a0[2 * r]);
-          a1[2 * r] = fma(l.x, x1, a1[2 * r]);
-          a0[2 * r + 1] = fma(l.y, x0, a0[2 * r + 1]);
-          a1[2 * r + 1] = fma(l.y, x1, a1[2 * r + 1]);
+        for (int nb = 0; nb < kNB; ++nb) b[nb] = bp[(size_t)nb * 8 * tld + 4 * ks];
+        if (ks < nks_up) {
+#pragma unroll
+          for (int nb = 0; nb < kNB; ++nb) dmma8x8x4(up[nb][0], up[nb][1], au, b[nb]);
+        }
+        if (lower_live) {
+#pragma unroll
+          for (int nb = 0; nb < kNB; ++nb) dmma8x8x4(lo[nb][0], lo[nb][1], al, b[nb]);
         }
       }
+      // sum of squares over the 16 rows: own rows first, then across the 8 row groups (lane bits 2..4)
 #pragma unroll
-      for (int r = 0; r < kRowBlk; ++r) { ss0 = fma(a0[r], a0[r], ss0); ss1 = fma(a1[r], a1[r], ss1); }
+      for (int nb = 0; nb < kNB; ++nb) {
+        double s0 = fma(up[nb][0], up[nb][0], lo[nb][0] * lo[nb][0]);
+        double s1 = fma(up[nb][1], up[nb][1], lo[nb][1] * lo[nb][1]);
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        if (g == 0) {
+          red[m * kPostCand + nb * 8 + 2 * t] = s0;
+          red[m * kPostCand + nb * 8 + 2 * t + 1] = s1;
+        }
+      }
     }
-    red[warp * kPostCand + lane] = ss0;
-    red[warp * kPostCand + lane + 32] = ss1;
     __syncthreads();
 
     if (threadIdx.x < in_tile) {
       const int c = threadIdx.x;
       double ss = 0.0;
-#pragma unroll
-      for (int w = 0; w < kPostWarps; ++w) ss += red[w * kPostCand + c];
+      for (int m = 0; m < n_blk; ++m) ss += red[m * kPostCand + c];
       const double var = p.variance - ss;
       const double sg = sqrt(var);
-      const double m = mus[c];
-      if (p.mu) p.mu[c0 + c] = m;
+      const double mval = mus[c];
+      if (p.mu) p.mu[c0 + c] = mval;
       if (p.sigma) p.sigma[c0 + c] = sg;
       if (p.acq) {
         double a;
         if (p.acq_kind == BOSOT_ACQ_EI) {
-          const double d = m - *p.cur_max - p.xi;
+          const double d = mval - *p.cur_max - p.xi;
           const double z = d / sg;
           a = d * norm_cdf(z) + sg * norm_pdf(z);
         } else if (p.acq_kind == BOSOT_ACQ_UCB) {
-          a = m + p.sqrt_ucb_beta * sg;
+          a = mval + p.sqrt_ucb_beta * sg;
         } else {
-          a = m;
+          a = mval;
         }
         p.acq[c0 + c] = a;
       }
@@ -167,30 +206,46 @@ __global__ void fp64_fma_probe_kernel(double* out, int iters) {
   if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // keep the chain alive
 }
 
-int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval, const double* d_LinvT, int ldl,
+__global__ void fp64_mma_probe_kernel(double* out, int iters) {
+  double d[8][2];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { d[k][0] = 0.0; d[k][1] = 0.0; }
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dmma8x8x4(d[k][0], d[k][1], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += d[k][0] + d[k][1];
+  if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval, const double* d_Linv, int ldl,
                      const double* d_beta, double mean_c, double variance, int acq_kind, const double* d_current_max,
                      double xi, double ucb_beta, double* d_mu, double* d_sigma, double* d_acq, cudaStream_t stream) {
-  if (!d_Kstar || !d_LinvT || !d_beta || n_cand < 0) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: null argument");
+  if (!d_Kstar || !d_Linv || !d_beta || n_cand < 0) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: null argument");
   if (n_eval < 1 || n_eval > BOSOT_MAX_EVAL || ld < n_eval) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: bad n_eval / ld");
-  if (ldl < n_eval || (ldl % kRowBlk) != 0 || (reinterpret_cast<uintptr_t>(d_LinvT) & 15))
-    return set_error(BOSOT_EINVAL, "bosot_posterior_acq: LinvT must be 16-byte aligned with ldl a multiple of 8 and >= n_eval");
+  if (ldl < n_eval || (ldl % kRowBlk) != 0)
+    return set_error(BOSOT_EINVAL, "bosot_posterior_acq: Linv must be [ldl][ldl] with ldl a multiple of 16 and >= n_eval");
   if (acq_kind == BOSOT_ACQ_EI && d_acq && !d_current_max) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: EI needs current_max");
   if (n_cand == 0) return BOSOT_OK;
 
   PostParams p;
   p.Kstar = d_Kstar; p.n_cand = n_cand; p.ld = ld; p.E = n_eval; p.ldl = ldl;
-  p.LinvT = d_LinvT; p.beta = d_beta; p.mean_c = mean_c; p.variance = variance;
+  p.Linv = d_Linv; p.beta = d_beta; p.mean_c = mean_c; p.variance = variance;
   p.acq_kind = acq_kind; p.cur_max = d_current_max; p.xi = xi; p.sqrt_ucb_beta = sqrt(ucb_beta);
   p.mu = d_mu; p.sigma = d_sigma; p.acq = d_acq;
 
-  const size_t smem = sizeof(double) * ((size_t)kPostCand * post_tile_ld(n_eval) + kPostWarps * kPostCand + kPostCand);
-  if (smem > 200 * 1024) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: n_eval too large for shared memory");
+  const int n_blk = (n_eval + kRowBlk - 1) / kRowBlk;
+  const size_t smem = sizeof(double) * ((size_t)kPostCand * post_tile_ld(n_eval) + (size_t)n_blk * kPostCand + kPostCand) + 16;
+  if (smem > 226 * 1024) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: n_eval too large for shared memory");
   static bool attr_set[64] = {false};
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   if (int rc = cuda_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return rc;
   if (!(dev < 64 && attr_set[dev])) {
-    if (int rc = cuda_check(cudaFuncSetAttribute(posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+    if (int rc = cuda_check(cudaFuncSetAttribute(posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024),
                             "cudaFuncSetAttribute(posterior_kernel)")) return rc;
     if (dev < 64) attr_set[dev] = true;
   }
@@ -213,6 +268,12 @@ extern "C" int bosot_max_f64(const double* d_x, int64_t n, double* d_out, void* 
   if (!d_x || !d_out || n < 1) return set_error(BOSOT_EINVAL, "bosot_max_f64: bad argument");
   max_f64_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_x, n, d_out);
   return after_launch("max_f64_kernel");
+}
+
+extern "C" int bosot_fp64_mma_probe(double* d_out, int n_blocks, int n_threads, int iters, void* stream) {
+  if (!d_out || n_blocks < 1 || n_threads < 32 || n_threads > 1024 || iters < 1) return set_error(BOSOT_EINVAL, "bosot_fp64_mma_probe: bad argument");
+  fp64_mma_probe_kernel<<<n_blocks, n_threads, 0, (cudaStream_t)stream>>>(d_out, iters);
+  return after_launch("fp64_mma_probe_kernel");
 }
 
 extern "C" int bosot_fp64_fma_probe(double* d_out, int n_blocks, int n_threads, int iters, void* stream) {

@@ -184,7 +184,7 @@ def sot_pairs(
 def gp_factorize(K_EE: torch.Tensor, noise_variance: float, err: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """Small E x E part of the posterior, left to cuSOLVER/cuBLAS via torch.linalg:
     Lm = chol(K_EE + s^2 I) (GPflow ``base_conditional``), returns
-    (LinvT padded to a leading dimension that is a multiple of 8, beta = (K_EE + s^2 I)^-1 err).
+    (Linv = Lm^-1 zero-padded to [ldl, ldl] with ldl a multiple of 16, beta = (K_EE + s^2 I)^-1 err).
     Raises like the reference's TF Cholesky when the matrix is not positive definite."""
     E = K_EE.shape[0]
     A = K_EE + noise_variance * torch.eye(E, dtype=torch.float64, device=K_EE.device)
@@ -192,17 +192,16 @@ def gp_factorize(K_EE: torch.Tensor, noise_variance: float, err: torch.Tensor) -
     if int(info) != 0:
         raise RuntimeError("Cholesky decomposition was not successful (leading minor %d not positive definite)" % int(info))
     eye = torch.eye(E, dtype=torch.float64, device=K_EE.device)
-    Linv = torch.linalg.solve_triangular(L, eye, upper=False)
-    ldl = (E + 7) // 8 * 8
-    LinvT = torch.zeros((E, ldl), dtype=torch.float64, device=K_EE.device)
-    LinvT[:, :E] = Linv.t()
+    ldl = (E + 15) // 16 * 16
+    Linv = torch.zeros((ldl, ldl), dtype=torch.float64, device=K_EE.device)
+    Linv[:E, :E] = torch.tril(torch.linalg.solve_triangular(L, eye, upper=False))
     beta = torch.cholesky_solve(err.reshape(E, 1), L).reshape(E).contiguous()
-    return LinvT, beta
+    return Linv, beta
 
 
 def posterior_acq(
     Kstar: torch.Tensor,
-    LinvT: torch.Tensor,
+    Linv: torch.Tensor,
     beta: torch.Tensor,
     mean_c: float,
     variance: float,
@@ -221,7 +220,7 @@ def posterior_acq(
     acq = torch.empty(n, dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
         rc = lib.bosot_posterior_acq(
-            Kstar.data_ptr(), n, Kstar.stride(0), E, LinvT.data_ptr(), LinvT.shape[1], beta.data_ptr(), float(mean_c), float(variance),
+            Kstar.data_ptr(), n, Kstar.stride(0), E, Linv.data_ptr(), Linv.shape[1], beta.data_ptr(), float(mean_c), float(variance),
             int(acq_kind), _ptr(current_max), float(xi), float(ucb_beta), mu.data_ptr(), sigma.data_ptr(), acq.data_ptr(), _stream(dev),
         )
     _lib.check(rc, "posterior_acq")
@@ -272,9 +271,9 @@ class AcquisitionEngine:
         self.n_eval = self.state.n_eval
         y = y.to(self.device, torch.float64).reshape(-1)
         self.K_EE = sot_pairs(eval_trees, self.state, self.weights, self.variance, self.lengthscale)["K"]
-        self.LinvT, self.beta = gp_factorize(self.K_EE, self.noise_variance, y - self.mean_c)
+        self.Linv, self.beta = gp_factorize(self.K_EE, self.noise_variance, y - self.mean_c)
         # posterior at the evaluated kernels -> current_max (bayesian_optimizer_objects.py:164-165)
-        self.mu_data, self.sigma_data, _ = posterior_acq(self.K_EE, self.LinvT, self.beta, self.mean_c, self.variance)
+        self.mu_data, self.sigma_data, _ = posterior_acq(self.K_EE, self.Linv, self.beta, self.mean_c, self.variance)
         self.current_max = max_f64(self.mu_data)
         self._work = None
         self._wdbl = _DBL3(*self.weights)
@@ -296,7 +295,7 @@ class AcquisitionEngine:
         with torch.cuda.device(self.device):
             rc = _lib.load().bosot_acquire_device(
                 trees.data_ptr(), n, C.byref(self.grammar.c_struct), self.state.blob.data_ptr(), self.n_eval, self._wdbl,
-                self.variance, self.lengthscale, self.LinvT.data_ptr(), self.LinvT.shape[1], self.beta.data_ptr(), self.mean_c,
+                self.variance, self.lengthscale, self.Linv.data_ptr(), self.Linv.shape[1], self.beta.data_ptr(), self.mean_c,
                 self.acq_kind, self.current_max.data_ptr(), self.xi, self.ucb_beta, w.data_ptr(), w.numel(),
                 mu.data_ptr(), sigma.data_ptr(), acq.data_ptr(), _stream(self.device),
             )
@@ -314,7 +313,7 @@ class AcquisitionEngine:
         with torch.cuda.device(self.device):
             rc = _lib.load().bosot_acquire_host(
                 h_trees.data_ptr(), n, C.byref(self.grammar.c_struct), self.state.blob.data_ptr(), self.n_eval, self._wdbl,
-                self.variance, self.lengthscale, self.LinvT.data_ptr(), self.LinvT.shape[1], self.beta.data_ptr(), self.mean_c,
+                self.variance, self.lengthscale, self.Linv.data_ptr(), self.Linv.shape[1], self.beta.data_ptr(), self.mean_c,
                 self.acq_kind, self.current_max.data_ptr(), self.xi, self.ucb_beta, w.data_ptr(), w.numel(),
                 _ptr(h_mu), _ptr(h_sigma), h_acq.data_ptr(), _stream(self.device),
             )

@@ -136,10 +136,9 @@ int bosot_sot_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar*
                     int32_t* d_status, void* stream);
 
 /* ---- GP posterior + acquisition -----------------------------------------------------
- * Inputs: K*[n_cand][ld] (rows = candidates), LinvT[n_eval][ldl] = transpose of the
- * inverse of the lower Cholesky factor of K_EE + noise*I (so column i of LinvT is row i
- * of L^-1; row-major, upper triangular; ldl >= n_eval a multiple of 8, columns >= n_eval
- * zero, base 16-byte aligned), beta[n_eval] = (K_EE + noise*I)^-1 (y - c).
+ * Inputs: K*[n_cand][ld] (rows = candidates), Linv[ldl][ldl] = inverse of the lower Cholesky
+ * factor of K_EE + noise*I (row-major, lower triangular, ldl >= n_eval a multiple of 16, rows and
+ * columns >= n_eval zero), beta[n_eval] = (K_EE + noise*I)^-1 (y - c).
  *   mu    = K* . beta + mean_c
  *   var   = variance - || L^-1 k* ||^2          (K_diag == variance: d(x,x) = 0 exactly)
  *   sigma = sqrt(var)                           (NaN if var < 0, as in the reference)
@@ -152,7 +151,7 @@ int bosot_sot_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar*
 #define BOSOT_ACQ_UCB 2
 
 int bosot_posterior_acq(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval,
-                        const double* d_LinvT, int ldl, const double* d_beta, double mean_c, double variance,
+                        const double* d_Linv, int ldl, const double* d_beta, double mean_c, double variance,
                         int acq_kind, const double* d_current_max, double xi, double ucb_beta,
                         double* d_mu, double* d_sigma, double* d_acq, void* stream);
 
@@ -169,7 +168,7 @@ size_t bosot_acquire_work_bytes(int64_t n_cand, int n_eval);
 int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const bosot_grammar* grammar,
                        const void* d_eval_blob, int n_eval, const double weights[3],
                        double variance, double lengthscale,
-                       const double* d_LinvT, int ldl, const double* d_beta, double mean_c,
+                       const double* d_Linv, int ldl, const double* d_beta, double mean_c,
                        int acq_kind, const double* d_current_max, double xi, double ucb_beta,
                        void* d_work, size_t work_bytes,
                        double* h_mu, double* h_sigma, double* h_acq, void* stream);
@@ -178,16 +177,18 @@ int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const bosot_gramm
 int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,
                          const void* d_eval_blob, int n_eval, const double weights[3],
                          double variance, double lengthscale,
-                         const double* d_LinvT, int ldl, const double* d_beta, double mean_c,
+                         const double* d_Linv, int ldl, const double* d_beta, double mean_c,
                          int acq_kind, const double* d_current_max, double xi, double ucb_beta,
                          void* d_work, size_t work_bytes,
                          double* d_mu, double* d_sigma, double* d_acq, void* stream);
 
 /* ---- measurement helpers -----------------------------------------------------------------
- * bosot_fp64_fma_probe: runs `iters` dependent-chain-free DFMA per thread on a full grid so
- * bench.py can measure this GPU's fp64 FMA ceiling (the secondary roofline of the posterior).
+ * bosot_fp64_fma_probe / bosot_fp64_mma_probe: run `iters` x 8 independent DFMA (resp. fp64
+ * mma.sync m8n8k4) per thread (resp. warp) on a full grid so bench.py can measure this GPU's
+ * fp64 ceilings (the secondary roofline of the posterior kernel).
  * bosot_kernel_launch_count: number of kernels this library has launched in this process. */
 int bosot_fp64_fma_probe(double* d_out, int n_blocks, int n_threads, int iters, void* stream);
+int bosot_fp64_mma_probe(double* d_out, int n_blocks, int n_threads, int iters, void* stream);
 int64_t bosot_kernel_launch_count(void);
 
 #ifdef __cplusplus
