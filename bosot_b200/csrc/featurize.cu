@@ -127,7 +127,7 @@ eval_build_kernel(uint8_t* __restrict__ blob, EvalLayout L, int n_dim_cols,
                   const uint8_t* __restrict__ n_nodes, const uint8_t* __restrict__ n_leaves,
                   const uint8_t* __restrict__ sub_n, const uint64_t* __restrict__ sub_id, const uint8_t* __restrict__ sub_cnt,
                   const uint8_t* __restrict__ path_n, const uint16_t* __restrict__ path_id, const uint8_t* __restrict__ path_cnt,
-                  const double* __restrict__ dimvec) {
+                  const uint8_t* __restrict__ sym_cnt, int n_symbols, const double* __restrict__ dimvec) {
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(blob + L.off_keys);
   uint2* range = reinterpret_cast<uint2*>(blob + L.off_range);
   uint32_t* post = reinterpret_cast<uint32_t*>(blob + L.off_post);
@@ -144,9 +144,19 @@ eval_build_kernel(uint8_t* __restrict__ blob, EvalLayout L, int n_dim_cols,
   }
   for (int s = tid; s < L.hash_cap; s += kBuildThreads) keys[s] = 0ULL;
   for (int s = tid; s < L.n_slots; s += kBuildThreads) { range[s] = make_uint2(0u, 0u); cursor[s] = 0u; }
+  double* b_rsub = reinterpret_cast<double*>(blob + L.off_rsub);
+  double* b_rpath = reinterpret_cast<double*>(blob + L.off_rpath);
+  uint8_t* symT = blob + L.off_symT;
   for (int e = tid; e < L.e_pad; e += kBuildThreads) {
-    b_nn[e] = e < E ? n_nodes[e] : 1;
-    b_nl[e] = e < E ? n_leaves[e] : 1;
+    const int nn = e < E ? n_nodes[e] : 1, nl = e < E ? n_leaves[e] : 1;
+    b_nn[e] = (uint8_t)nn;
+    b_nl[e] = (uint8_t)nl;
+    b_rsub[e] = 1.0 / (double)(nn ? nn : 1);
+    b_rpath[e] = 1.0 / (double)(nl ? nl : 1);
+  }
+  for (int x = tid; x < BOSOT_MAX_SYMBOLS * L.e_pad; x += kBuildThreads) {
+    const int s = x / L.e_pad, e = x % L.e_pad;
+    symT[x] = (s < n_symbols && e < E) ? sym_cnt[(size_t)e * n_symbols + s] : 0;
   }
   for (int x = tid; x < BOSOT_MAX_DIM_COLS * L.e_pad; x += kBuildThreads) {
     const int c = x / L.e_pad, e = x % L.e_pad;
@@ -155,8 +165,7 @@ eval_build_kernel(uint8_t* __restrict__ blob, EvalLayout L, int n_dim_cols,
   __syncthreads();
 
   // pass 1: slot of every (tree, feature); count per slot (range.y)
-  auto slot_of_sub = [&](uint64_t id) -> uint32_t {
-    if (!(id >> 63)) return (uint32_t)L.hash_cap + (uint32_t)(id - 1);  // leaf class: direct by symbol
+  auto slot_of_sub = [&](uint64_t id) -> uint32_t {  // operator classes only (bit 63 set)
     uint32_t s = hash_slot(id, L.hash_cap);
     while (true) {
       const unsigned long long prev = atomicCAS(&keys[s], 0ULL, (unsigned long long)id);
@@ -166,7 +175,7 @@ eval_build_kernel(uint8_t* __restrict__ blob, EvalLayout L, int n_dim_cols,
   };
   for (int x = tid; x < E * kMaxNodes; x += kBuildThreads) {
     const int e = x / kMaxNodes, f = x % kMaxNodes;
-    if (f < sub_n[e]) atomicAdd(&range[slot_of_sub(sub_id[x])].y, 1u);
+    if (f < sub_n[e] && (sub_id[x] >> 63)) atomicAdd(&range[slot_of_sub(sub_id[x])].y, 1u);  // leaf classes live in symT
   }
   for (int x = tid; x < E * kMaxLeaves; x += kBuildThreads) {
     const int e = x / kMaxLeaves, f = x % kMaxLeaves;
@@ -195,7 +204,7 @@ eval_build_kernel(uint8_t* __restrict__ blob, EvalLayout L, int n_dim_cols,
   // pass 3: fill postings (order inside a posting list is irrelevant: one posting per tree)
   for (int x = tid; x < E * kMaxNodes; x += kBuildThreads) {
     const int e = x / kMaxNodes, f = x % kMaxNodes;
-    if (f < sub_n[e]) {
+    if (f < sub_n[e] && (sub_id[x] >> 63)) {
       const uint32_t s = slot_of_sub(sub_id[x]);
       const uint32_t p = atomicAdd(&cursor[s], 1u);
       post[range[s].x + p] = pack_posting((uint32_t)e, sub_cnt[x], n_nodes[e]);
@@ -213,7 +222,7 @@ eval_build_kernel(uint8_t* __restrict__ blob, EvalLayout L, int n_dim_cols,
 
 // scratch appended to the blob for the featurised evaluated set
 struct EvalScratch {
-  size_t n_nodes, n_leaves, sub_n, sub_id, sub_cnt, path_n, path_id, path_cnt, dimvec, total;
+  size_t n_nodes, n_leaves, sub_n, sub_id, sub_cnt, path_n, path_id, path_cnt, sym_cnt, dimvec, total;
 };
 static EvalScratch eval_scratch(int E, size_t base) {
   EvalScratch S;
@@ -223,6 +232,7 @@ static EvalScratch eval_scratch(int E, size_t base) {
   S.path_id = o;  o = align16(o + sizeof(uint16_t) * (size_t)E * kMaxLeaves);
   S.sub_cnt = o;  o = align16(o + (size_t)E * kMaxNodes);
   S.path_cnt = o; o = align16(o + (size_t)E * kMaxLeaves);
+  S.sym_cnt = o;  o = align16(o + (size_t)E * BOSOT_MAX_SYMBOLS);
   S.n_nodes = o;  o = align16(o + (size_t)E);
   S.n_leaves = o; o = align16(o + (size_t)E);
   S.sub_n = o;    o = align16(o + (size_t)E);
@@ -273,13 +283,13 @@ extern "C" int bosot_eval_build(const uint8_t* d_trees, int n_eval, const bosot_
   featurize_kernel<<<blocks, kFeatThreads, kFeatThreads * kRecBytes, st>>>(
       d_trees, n_eval, *grammar, b + S.n_nodes, b + S.n_leaves, b + S.sub_n,
       reinterpret_cast<uint64_t*>(b + S.sub_id), b + S.sub_cnt, b + S.path_n,
-      reinterpret_cast<uint16_t*>(b + S.path_id), b + S.path_cnt, nullptr,
+      reinterpret_cast<uint16_t*>(b + S.path_id), b + S.path_cnt, b + S.sym_cnt,
       reinterpret_cast<double*>(b + S.dimvec), d_status);
   if (int rc = after_launch("featurize_kernel(eval)")) return rc;
   eval_build_kernel<<<1, kBuildThreads, 0, st>>>(
       b, L, grammar->n_dim_cols, b + S.n_nodes, b + S.n_leaves, b + S.sub_n,
       reinterpret_cast<const uint64_t*>(b + S.sub_id), b + S.sub_cnt, b + S.path_n,
-      reinterpret_cast<const uint16_t*>(b + S.path_id), b + S.path_cnt,
+      reinterpret_cast<const uint16_t*>(b + S.path_id), b + S.path_cnt, b + S.sym_cnt, grammar->n_symbols,
       reinterpret_cast<const double*>(b + S.dimvec));
   return after_launch("eval_build_kernel");
 }

@@ -128,12 +128,15 @@ struct EvalLayout {
   int e_pad;      // E rounded up to 32
   int hash_cap;   // power of two >= 2 * 31 * E (load factor <= 0.5)
   int n_slots;    // hash_cap + 64 + 64*64 : unified slot space (hash | leaf symbol | path id)
-  int max_post;   // 95 * E
+  int max_post;   // 63 * E
   size_t off_keys;     // uint64 [hash_cap]
   size_t off_range;    // uint2  [n_slots]   (begin, length) into postings
   size_t off_post;     // uint32 [max_post]  e | count << 16 | total << 24
-  size_t off_nnodes;   // uint8  [e_pad]
-  size_t off_nleaves;  // uint8  [e_pad]
+  size_t off_nnodes;   // uint8  [e_pad]     SUBTREES total (nodes)
+  size_t off_nleaves;  // uint8  [e_pad]     PATHS total (leaves)
+  size_t off_rsub;     // double [e_pad]     1 / nodes
+  size_t off_rpath;    // double [e_pad]     1 / leaves
+  size_t off_symT;     // uint8  [BOSOT_MAX_SYMBOLS][e_pad]  leaf count per symbol, transposed
   size_t off_dimT;     // double [BOSOT_MAX_DIM_COLS][e_pad]  transposed dim-wise matrix
   size_t off_cursor;   // uint32 [n_slots]   build scratch
   size_t total;
@@ -149,13 +152,16 @@ __host__ __device__ inline EvalLayout eval_layout(int n_eval) {
   while (cap < 2 * kMaxInternal * n_eval) cap <<= 1;
   L.hash_cap = cap;
   L.n_slots = cap + BOSOT_MAX_SYMBOLS + BOSOT_MAX_SYMBOLS * kPathCodes;
-  L.max_post = (kMaxInternal + 2 * kMaxLeaves) * n_eval;
+  L.max_post = (kMaxInternal + kMaxLeaves) * n_eval;  // operator classes + reduced paths (leaf classes are dense)
   size_t o = 64;  // header
   L.off_keys = o;      o = align16(o + sizeof(uint64_t) * (size_t)cap);
   L.off_range = o;     o = align16(o + sizeof(uint2) * (size_t)L.n_slots);
   L.off_post = o;      o = align16(o + sizeof(uint32_t) * (size_t)L.max_post);
   L.off_nnodes = o;    o = align16(o + (size_t)L.e_pad);
   L.off_nleaves = o;   o = align16(o + (size_t)L.e_pad);
+  L.off_rsub = o;      o = align16(o + sizeof(double) * (size_t)L.e_pad);
+  L.off_rpath = o;     o = align16(o + sizeof(double) * (size_t)L.e_pad);
+  L.off_symT = o;      o = align16(o + (size_t)BOSOT_MAX_SYMBOLS * L.e_pad);
   L.off_dimT = o;      o = align16(o + sizeof(double) * (size_t)BOSOT_MAX_DIM_COLS * L.e_pad);
   L.off_cursor = o;    o = align16(o + sizeof(uint32_t) * (size_t)L.n_slots);
   L.total = o;

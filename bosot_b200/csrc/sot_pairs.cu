@@ -11,12 +11,14 @@
 // features present in BOTH trees contribute, so one candidate costs O(matches), found
 // through the evaluated set's postings, instead of O(E * F).
 //
-// Work decomposition (one warp owns 32 consecutive candidates at a time):
+// Work decomposition (one warp owns kChunk consecutive candidates at a time):
 //   phase A  thread-per-tree : scan_tree() -> class ids, leaf symbols, reduced path codes (smem)
-//   phase B  warp-per-tree   : dedupe with __match_any_sync, look the features up (hash table for
-//                              operator classes, direct tables for leaf symbols and paths),
-//                              walk the postings, accumulate M_sub / M_path per evaluated tree
-//   phase C  lane-per-pair   : DIM_WISE dense L1, combine with the alpha weights, exp, store
+//   phase B  warp-per-tree   : dedupe with __match_any_sync; operator classes go through the hash
+//                              table, reduced paths through a direct table, and their (short)
+//                              posting lists are walked into shared-memory accumulators
+//   phase C  lane-per-pair   : every lane owns R evaluated trees in registers: leaf-symbol
+//                              classes (dense: most symbols occur in most trees) against the
+//                              transposed count table, DIM_WISE dense L1, combine, exp, store
 #include "sot_common.cuh"
 #include "launch.cuh"
 
@@ -24,6 +26,9 @@ namespace bosot {
 
 constexpr int kPairWarps = 4;
 constexpr int kPairThreads = kPairWarps * 32;
+constexpr int kChunk = 16;  // trees scanned per warp pass: half the lanes idle in phase A (5% of the
+                            // work) in exchange for half the shared memory => twice the resident warps
+constexpr int kR = 8;       // evaluated trees per lane per register tile (covers E <= 256 in one pass)
 
 __constant__ double c_recip[64];  // 1/T for T = 1..63 ([0] unused)
 
@@ -33,7 +38,7 @@ struct PairParams {
   const uint8_t* blob;
   EvalLayout L;
   double w_dim, w_path, w_sub;
-  double variance, lengthscale_sq;
+  double variance, neg_inv_lsq;  // -1 / lengthscale^2
   double* K;
   double* D;
   double* Df;
@@ -41,12 +46,13 @@ struct PairParams {
   int32_t* status;
 };
 
-// per-warp shared memory: 32 tree records, accumulators, candidate dim-wise vector, symbol counts
+// per-warp shared memory: kChunk tree records, candidate dim-wise vector, accumulators, symbol counts
 __host__ __device__ inline size_t pair_warp_smem(int e_pad) {
-  return (size_t)32 * kRecBytes + sizeof(uint32_t) * (size_t)e_pad + sizeof(double) * BOSOT_MAX_DIM_COLS +
+  return (size_t)kChunk * kRecBytes + sizeof(double) * BOSOT_MAX_DIM_COLS + sizeof(uint32_t) * (size_t)e_pad +
          sizeof(uint32_t) * (BOSOT_MAX_SYMBOLS + BOSOT_MAX_BLOCKS);
 }
 
+template <bool kExtra>  // kExtra: also write D and/or Df
 __global__ void __launch_bounds__(kPairThreads)
 sot_pair_kernel(PairParams p, bosot_grammar g) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -57,9 +63,9 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   const unsigned full = 0xffffffffu;
 
   uint8_t* wbase = smem + (size_t)warp * pair_warp_smem(e_pad);
-  uint8_t* recs = wbase;                                                   // 32 * 424 B
-  double* avec = reinterpret_cast<double*>(wbase + 32 * kRecBytes);        // candidate DIM_WISE vector
-  uint32_t* acc = reinterpret_cast<uint32_t*>(avec + BOSOT_MAX_DIM_COLS);  // M_sub | M_path << 16 per e
+  uint8_t* recs = wbase;                                                   // kChunk * 424 B
+  double* avec = reinterpret_cast<double*>(wbase + kChunk * kRecBytes);    // candidate DIM_WISE vector
+  uint32_t* acc = reinterpret_cast<uint32_t*>(avec + BOSOT_MAX_DIM_COLS);  // M_sub(ops) | M_path << 16 per e
   uint32_t* scnt = acc + e_pad;                                            // leaf count per symbol
   uint32_t* btot = scnt + BOSOT_MAX_SYMBOLS;                               // leaf count per block
 
@@ -68,17 +74,21 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   const uint32_t* post = reinterpret_cast<const uint32_t*>(p.blob + p.L.off_post);
   const uint8_t* e_nn = p.blob + p.L.off_nnodes;
   const uint8_t* e_nl = p.blob + p.L.off_nleaves;
+  const double* e_rsub = reinterpret_cast<const double*>(p.blob + p.L.off_rsub);
+  const double* e_rpath = reinterpret_cast<const double*>(p.blob + p.L.off_rpath);
+  const uint8_t* symT = p.blob + p.L.off_symT;
   const double* dimT = reinterpret_cast<const double*>(p.blob + p.L.off_dimT);
   const int hash_cap = p.L.hash_cap;
   const int F = g.n_dim_cols;
+  const size_t plane = (size_t)p.n_cand * p.ld;
 
-  const int64_t n_chunks = (p.n_cand + 31) >> 5;
+  const int64_t n_chunks = (p.n_cand + kChunk - 1) / kChunk;
   for (int64_t chunk = (int64_t)blockIdx.x * kPairWarps + warp; chunk < n_chunks;
        chunk += (int64_t)gridDim.x * kPairWarps) {
-    const int64_t c0 = chunk << 5;
-    const int in_chunk = (int)min((int64_t)32, p.n_cand - c0);
+    const int64_t c0 = chunk * kChunk;
+    const int in_chunk = (int)min((int64_t)kChunk, p.n_cand - c0);
 
-    // ---- phase A: coalesced load of 32 records (2 KB), then one thread scans one tree
+    // ---- phase A: coalesced load of kChunk records, then one thread scans one tree
     __syncwarp();
     for (int w = lane; w < in_chunk * 4; w += 32) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.trees + c0 * kTreeBytes) + w);
@@ -98,14 +108,14 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
       const uint8_t* rj = recs + j * kRecBytes;
       const int nn = rj[kRecMeta + 0], nl = rj[kRecMeta + 1], ni = rj[kRecMeta + 2];
       const bool bad = rj[kRecMeta + 3] != 0;
-      const int64_t row = (c0 + j) * p.ld;
+      const size_t row = (size_t)(c0 + j) * p.ld;
 
       if (bad) {  // malformed record: poison the row, status already written
         const double qnan = __longlong_as_double(0x7ff8000000000000LL);
         for (int e = lane; e < E; e += 32) {
           if (p.K) p.K[row + e] = qnan;
           if (p.D) p.D[row + e] = qnan;
-          if (p.Df) { p.Df[row + e] = qnan; p.Df[p.n_cand * p.ld + row + e] = qnan; p.Df[2 * p.n_cand * p.ld + row + e] = qnan; }
+          if (p.Df) { p.Df[row + e] = qnan; p.Df[plane + row + e] = qnan; p.Df[2 * plane + row + e] = qnan; }
         }
         continue;
       }
@@ -115,7 +125,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
       for (int c = lane; c < F; c += 32) avec[c] = 0.0;
       __syncwarp();
 
-      // leaves: SUBTREES leaf classes (key = symbol) and PATHS (key = symbol * 64 + code)
+      // leaves: symbol multiplicities (SUBTREES leaf classes, DIM_WISE) and PATHS (key = symbol * 64 + code)
       const bool is_leaf = lane < nl;
       const uint32_t sym = is_leaf ? rj[kRecLeafSym + lane] : 0u;
       const uint32_t pid = is_leaf ? sym * kPathCodes + rj[kRecLeafCode + lane] : 0u;
@@ -123,13 +133,14 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
       const unsigned m_pid = __match_any_sync(full, is_leaf ? pid : 0x10000u + lane);
       const bool lead_sym = is_leaf && (__ffs(m_sym) - 1 == lane);
       const bool lead_pid = is_leaf && (__ffs(m_pid) - 1 == lane);
-      uint2 r_sym = make_uint2(0u, 0u), r_pid = make_uint2(0u, 0u);
+      const uint32_t cnt_sym = (uint32_t)__popc(m_sym);
+      uint2 r_pid = make_uint2(0u, 0u);
       if (lead_sym) {
-        r_sym = __ldg(&range[hash_cap + sym]);
-        scnt[sym] = __popc(m_sym);
-        if (g.sym_block[sym] >= 0) atomicAdd(&btot[g.sym_block[sym]], (uint32_t)__popc(m_sym));
+        scnt[sym] = cnt_sym;
+        if (g.sym_block[sym] >= 0) atomicAdd(&btot[g.sym_block[sym]], cnt_sym);
       }
       if (lead_pid) r_pid = __ldg(&range[hash_cap + BOSOT_MAX_SYMBOLS + pid]);
+      const unsigned sym_leads = __ballot_sync(full, lead_sym);
 
       // operator nodes: SUBTREES classes through the hash table
       const bool is_int = lane < ni;
@@ -175,34 +186,70 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
           __syncwarp();
         }
       };
-      walk(r_sym, (uint32_t)__popc(m_sym), (uint32_t)nn, 0);
       walk(r_int, (uint32_t)__popc(m_id), (uint32_t)nn, 0);
       walk(r_pid, (uint32_t)__popc(m_pid), (uint32_t)nl, 16);
       __syncwarp();
 
-      // ---- phase C: one lane per evaluated tree
+      // ---- phase C: register tiles of kR evaluated trees per lane
       const double rTa_sub = c_recip[nn], rTa_path = c_recip[nl];
-      for (int e = lane; e < E; e += 32) {
-        const uint32_t a = acc[e];
-        const uint32_t m_sub = a & 0xffffu, m_path = a >> 16;
-        const uint32_t tb_sub = __ldg(&e_nn[e]), tb_path = __ldg(&e_nl[e]);
-        // 2 - 2*M/(Ta*Tb); exactly 0 when the histograms coincide; (1/Ta)*(1/Tb) first keeps D(a,b) == D(b,a) bitwise
-        const double d_sub = (m_sub == (uint32_t)nn * tb_sub)
-                                 ? 0.0 : fma(-2.0, (double)m_sub * (rTa_sub * c_recip[tb_sub]), 2.0);
-        const double d_path = (m_path == (uint32_t)nl * tb_path)
-                                  ? 0.0 : fma(-2.0, (double)m_path * (rTa_path * c_recip[tb_path]), 2.0);
-        double d_dim = 0.0;
-        for (int c = 0; c < F; ++c) d_dim += fabs(avec[c] - __ldg(&dimT[(size_t)c * e_pad + e]));
-        // sum_f w_f * D_f in feature_type_list order (kernel_kernel_grammar_tree.py:159-161)
-        const double d = __dadd_rn(__dadd_rn(__dmul_rn(p.w_dim, d_dim), __dmul_rn(p.w_path, d_path)),
-                                   __dmul_rn(p.w_sub, d_sub));
-        if (p.Df) {
-          p.Df[row + e] = d_dim;
-          p.Df[p.n_cand * p.ld + row + e] = d_path;
-          p.Df[2 * p.n_cand * p.ld + row + e] = d_sub;
+      for (int e0 = 0; e0 < E; e0 += 32 * kR) {
+        const int eb = e0 + lane;  // lane's first evaluated tree; its r-th is eb + 32 r (padded arrays: always in bounds
+                                   // of e_pad as long as eb + 32 r < e_pad)
+        uint32_t msub[kR], tbs[kR];
+        double ddim[kR];
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+          const int e = min(eb + 32 * r, e_pad - 1);
+          tbs[r] = __ldg(&e_nn[e]);
+          msub[r] = 0u;
+          ddim[r] = 0.0;
         }
-        if (p.D) p.D[row + e] = d;
-        if (p.K) p.K[row + e] = p.variance * exp(-1.0 * d / p.lengthscale_sq);
+        // SUBTREES, leaf classes: sum over the candidate's distinct symbols of min(ca * Tb, cb * Ta)
+        for (unsigned todo = sym_leads; todo;) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const uint32_t s = __shfl_sync(full, sym, src);
+          const uint32_t ca = __shfl_sync(full, cnt_sym, src);
+          const uint8_t* col = symT + (size_t)s * e_pad;
+#pragma unroll
+          for (int r = 0; r < kR; ++r) {
+            const int e = min(eb + 32 * r, e_pad - 1);
+            const uint32_t cb = __ldg(&col[e]);
+            msub[r] += min(ca * tbs[r], cb * (uint32_t)nn);
+          }
+        }
+        // DIM_WISE: dense L1 over the d * (kinds + 1) columns, column-outer so the candidate value is read once
+        for (int c = 0; c < F; ++c) {
+          const double a = avec[c];
+          const double* col = dimT + (size_t)c * e_pad;
+#pragma unroll
+          for (int r = 0; r < kR; ++r) {
+            const int e = min(eb + 32 * r, e_pad - 1);
+            ddim[r] += fabs(a - __ldg(&col[e]));
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+          const int e = eb + 32 * r;
+          if (e < E) {
+            const uint32_t a = acc[e];
+            const uint32_t m_sub = msub[r] + (a & 0xffffu), m_path = a >> 16;
+            const uint32_t tb_path = __ldg(&e_nl[e]);
+            // 2 - 2*M/(Ta*Tb); exactly 0 when the histograms coincide; (1/Ta)*(1/Tb) first keeps D(a,b) == D(b,a) bitwise
+            const double d_sub = (m_sub == (uint32_t)nn * tbs[r])
+                                     ? 0.0 : fma(-2.0, (double)m_sub * (rTa_sub * __ldg(&e_rsub[e])), 2.0);
+            const double d_path = (m_path == (uint32_t)nl * tb_path)
+                                      ? 0.0 : fma(-2.0, (double)m_path * (rTa_path * __ldg(&e_rpath[e])), 2.0);
+            // sum_f w_f * D_f in feature_type_list order (kernel_kernel_grammar_tree.py:159-161)
+            const double d = __dadd_rn(__dadd_rn(__dmul_rn(p.w_dim, ddim[r]), __dmul_rn(p.w_path, d_path)),
+                                       __dmul_rn(p.w_sub, d_sub));
+            if (kExtra) {
+              if (p.Df) { p.Df[row + e] = ddim[r]; p.Df[plane + row + e] = d_path; p.Df[2 * plane + row + e] = d_sub; }
+              if (p.D) p.D[row + e] = d;
+            }
+            if (p.K) p.K[row + e] = p.variance * exp(d * p.neg_inv_lsq);
+          }
+        }
       }
       __syncwarp();
     }
@@ -243,7 +290,7 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   p.w_path = weights[1];
   p.w_sub = weights[2];
   p.variance = variance;
-  p.lengthscale_sq = lengthscale * lengthscale;
+  p.neg_inv_lsq = -1.0 / (lengthscale * lengthscale);
   p.K = d_K;
   p.D = d_D;
   p.Df = d_Df;
@@ -255,21 +302,25 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   if (int rc = cuda_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return rc;
+  const bool extra = d_D != nullptr || d_Df != nullptr;
+  auto kernel = extra ? sot_pair_kernel<true> : sot_pair_kernel<false>;
   if (!(dev < 64 && attr_set[dev])) {
-    if (int rc = cuda_check(cudaFuncSetAttribute(sot_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+    if (int rc = cuda_check(cudaFuncSetAttribute(sot_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                            "cudaFuncSetAttribute(sot_pair_kernel)")) return rc;
+    if (int rc = cuda_check(cudaFuncSetAttribute(sot_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
                             "cudaFuncSetAttribute(sot_pair_kernel)")) return rc;
     if (dev < 64) attr_set[dev] = true;
   }
   if (smem > 200 * 1024) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: n_eval too large for shared memory");
   int per_sm = 1;
-  if (int rc = cuda_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sot_pair_kernel, kPairThreads, smem),
+  if (int rc = cuda_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPairThreads, smem),
                           "cudaOccupancyMaxActiveBlocksPerMultiprocessor")) return rc;
   if (per_sm < 1) per_sm = 1;
   // grid: a whole number of waves (SMs x resident CTAs), persistent loop over 32-tree chunks
-  const int64_t want = ((n_cand + 31) / 32 + kPairWarps - 1) / kPairWarps;
+  const int64_t want = ((n_cand + kChunk - 1) / kChunk + kPairWarps - 1) / kPairWarps;
   const int64_t wave = (int64_t)sms * per_sm;
   const int64_t grid = want < wave ? want : wave;
-  sot_pair_kernel<<<(unsigned)grid, kPairThreads, smem, stream>>>(p, *grammar);
+  kernel<<<(unsigned)grid, kPairThreads, smem, stream>>>(p, *grammar);
   return after_launch("sot_pair_kernel");
 }
 
