@@ -1,0 +1,2 @@
+"""Mirror of bosot/configs/kernels/kernel_grammar_generators/cks_high_dim_generator_config.py."""
+from .generator_configs import *  # noqa: F401,F403

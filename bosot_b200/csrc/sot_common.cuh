@@ -125,7 +125,7 @@ __device__ __forceinline__ int scan_tree(uint8_t* rec, int n_symbols) {
 // ---- evaluated-set blob layout (all offsets 16-byte aligned) ---------------------------
 struct EvalLayout {
   int n_eval;     // E
-  int e_pad;      // E rounded up to 32
+  int e_pad;      // E rounded up to 32; beyond 256 evaluated trees rounded up to 256 (whole register tiles)
   int hash_cap;   // power of two >= 2 * 31 * E (load factor <= 0.5)
   int n_slots;    // hash_cap + 64 + 64*64 : unified slot space (hash | leaf symbol | path id)
   int max_post;   // 63 * E
@@ -147,7 +147,7 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t
 __host__ __device__ inline EvalLayout eval_layout(int n_eval) {
   EvalLayout L;
   L.n_eval = n_eval;
-  L.e_pad = (n_eval + 31) & ~31;
+  L.e_pad = n_eval <= 256 ? ((n_eval + 31) & ~31) : ((n_eval + 255) & ~255);
   int cap = 64;
   while (cap < 2 * kMaxInternal * n_eval) cap <<= 1;
   L.hash_cap = cap;

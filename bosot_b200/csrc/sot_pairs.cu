@@ -28,7 +28,7 @@ constexpr int kPairWarps = 4;
 constexpr int kPairThreads = kPairWarps * 32;
 constexpr int kChunk = 16;  // trees scanned per warp pass: half the lanes idle in phase A (5% of the
                             // work) in exchange for half the shared memory => twice the resident warps
-constexpr int kR = 8;       // evaluated trees per lane per register tile (covers E <= 256 in one pass)
+constexpr int kMaxR = 8;    // evaluated trees per lane per register tile (E <= 256 in one pass, else tiles of 256)
 
 __constant__ double c_recip[64];  // 1/T for T = 1..63 ([0] unused)
 
@@ -52,7 +52,34 @@ __host__ __device__ inline size_t pair_warp_smem(int e_pad) {
          sizeof(uint32_t) * (BOSOT_MAX_SYMBOLS + BOSOT_MAX_BLOCKS);
 }
 
-template <bool kExtra>  // kExtra: also write D and/or Df
+// exp(x) for x <= 0 (the Gram argument -d / l^2): Cody-Waite reduction by ln 2, degree-13 Taylor
+// polynomial on |r| <= ln2 / 2 (truncation 4e-18 relative), scaling through the exponent field.
+// About half the instructions of the general exp(); the denormal / underflow tail takes the slow path.
+__device__ __forceinline__ double exp_nonpos(double x) {
+  const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
+  const int n = __double2loint(t);
+  const double nf = t - 6755399441055744.0;
+  double r = fma(nf, -6.93147180369123816490e-01, x);
+  r = fma(nf, -1.90821492927058770002e-10, r);
+  double q = 1.6059043836821613e-10;           // 1/13!
+  q = fma(q, r, 2.08767569878681e-09);         // 1/12!
+  q = fma(q, r, 2.505210838544172e-08);        // 1/11!
+  q = fma(q, r, 2.755731922398589e-07);        // 1/10!
+  q = fma(q, r, 2.7557319223985893e-06);       // 1/9!
+  q = fma(q, r, 2.48015873015873e-05);         // 1/8!
+  q = fma(q, r, 1.984126984126984e-04);        // 1/7!
+  q = fma(q, r, 1.388888888888889e-03);        // 1/6!
+  q = fma(q, r, 8.333333333333333e-03);        // 1/5!
+  q = fma(q, r, 4.1666666666666664e-02);       // 1/4!
+  q = fma(q, r, 1.6666666666666666e-01);       // 1/3!
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  q = fma(q, r, 1.0);
+  if (n < -1021 || !(x <= 0.0)) return exp(x);  // underflow tail, NaN
+  return __hiloint2double(__double2hiint(q) + n * 1048576, __double2loint(q));
+}
+
+template <int R, bool kExtra>  // R: evaluated trees per lane per tile; kExtra: also write D and/or Df
 __global__ void __launch_bounds__(kPairThreads)
 sot_pair_kernel(PairParams p, bosot_grammar g) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -190,19 +217,20 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
       walk(r_pid, (uint32_t)__popc(m_pid), (uint32_t)nl, 16);
       __syncwarp();
 
-      // ---- phase C: register tiles of kR evaluated trees per lane
+      // ---- phase C: register tiles of R evaluated trees per lane (tree e = e0 + lane + 32 r)
       const double rTa_sub = c_recip[nn], rTa_path = c_recip[nl];
-      for (int e0 = 0; e0 < E; e0 += 32 * kR) {
-        const int eb = e0 + lane;  // lane's first evaluated tree; its r-th is eb + 32 r (padded arrays: always in bounds
-                                   // of e_pad as long as eb + 32 r < e_pad)
-        uint32_t msub[kR], tbs[kR];
-        double ddim[kR];
+      for (int e0 = 0; e0 < E; e0 += 32 * R) {
+        const int eb = e0 + lane;  // e_pad is a whole number of tiles: eb + 32 r < e_pad, padded arrays stay in bounds
+        uint32_t msub[R], tbs[R];
+        double ddim[R];
+        {
+          const uint8_t* nnp = e_nn + eb;
 #pragma unroll
-        for (int r = 0; r < kR; ++r) {
-          const int e = min(eb + 32 * r, e_pad - 1);
-          tbs[r] = __ldg(&e_nn[e]);
-          msub[r] = 0u;
-          ddim[r] = 0.0;
+          for (int r = 0; r < R; ++r) {
+            tbs[r] = __ldg(nnp + 32 * r);
+            msub[r] = 0u;
+            ddim[r] = 0.0;
+          }
         }
         // SUBTREES, leaf classes: sum over the candidate's distinct symbols of min(ca * Tb, cb * Ta)
         for (unsigned todo = sym_leads; todo;) {
@@ -210,26 +238,21 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
           todo &= todo - 1;
           const uint32_t s = __shfl_sync(full, sym, src);
           const uint32_t ca = __shfl_sync(full, cnt_sym, src);
-          const uint8_t* col = symT + (size_t)s * e_pad;
+          const uint8_t* col = symT + s * (uint32_t)e_pad + eb;
 #pragma unroll
-          for (int r = 0; r < kR; ++r) {
-            const int e = min(eb + 32 * r, e_pad - 1);
-            const uint32_t cb = __ldg(&col[e]);
-            msub[r] += min(ca * tbs[r], cb * (uint32_t)nn);
-          }
+          for (int r = 0; r < R; ++r) msub[r] += min(ca * tbs[r], (uint32_t)__ldg(col + 32 * r) * (uint32_t)nn);
         }
         // DIM_WISE: dense L1 over the d * (kinds + 1) columns, column-outer so the candidate value is read once
-        for (int c = 0; c < F; ++c) {
-          const double a = avec[c];
-          const double* col = dimT + (size_t)c * e_pad;
+        {
+          const double* col = dimT + eb;
+          for (int c = 0; c < F; ++c, col += e_pad) {
+            const double a = avec[c];
 #pragma unroll
-          for (int r = 0; r < kR; ++r) {
-            const int e = min(eb + 32 * r, e_pad - 1);
-            ddim[r] += fabs(a - __ldg(&col[e]));
+            for (int r = 0; r < R; ++r) ddim[r] += fabs(a - __ldg(col + 32 * r));
           }
         }
 #pragma unroll
-        for (int r = 0; r < kR; ++r) {
+        for (int r = 0; r < R; ++r) {
           const int e = eb + 32 * r;
           if (e < E) {
             const uint32_t a = acc[e];
@@ -247,7 +270,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
               if (p.Df) { p.Df[row + e] = ddim[r]; p.Df[plane + row + e] = d_path; p.Df[2 * plane + row + e] = d_sub; }
               if (p.D) p.D[row + e] = d;
             }
-            if (p.K) p.K[row + e] = p.variance * exp(d * p.neg_inv_lsq);
+            if (p.K) p.K[row + e] = p.variance * exp_nonpos(d * p.neg_inv_lsq);
           }
         }
       }
@@ -303,12 +326,20 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   cudaGetDevice(&dev);
   if (int rc = cuda_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return rc;
   const bool extra = d_D != nullptr || d_Df != nullptr;
-  auto kernel = extra ? sot_pair_kernel<true> : sot_pair_kernel<false>;
+  const int rounds = p.L.e_pad / 32;
+  const int R = rounds < kMaxR ? rounds : kMaxR;
+  using KernelFn = void (*)(PairParams, bosot_grammar);
+  static const KernelFn table[kMaxR][2] = {
+      {sot_pair_kernel<1, false>, sot_pair_kernel<1, true>}, {sot_pair_kernel<2, false>, sot_pair_kernel<2, true>},
+      {sot_pair_kernel<3, false>, sot_pair_kernel<3, true>}, {sot_pair_kernel<4, false>, sot_pair_kernel<4, true>},
+      {sot_pair_kernel<5, false>, sot_pair_kernel<5, true>}, {sot_pair_kernel<6, false>, sot_pair_kernel<6, true>},
+      {sot_pair_kernel<7, false>, sot_pair_kernel<7, true>}, {sot_pair_kernel<8, false>, sot_pair_kernel<8, true>}};
+  KernelFn kernel = table[R - 1][extra ? 1 : 0];
   if (!(dev < 64 && attr_set[dev])) {
-    if (int rc = cuda_check(cudaFuncSetAttribute(sot_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
-                            "cudaFuncSetAttribute(sot_pair_kernel)")) return rc;
-    if (int rc = cuda_check(cudaFuncSetAttribute(sot_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
-                            "cudaFuncSetAttribute(sot_pair_kernel)")) return rc;
+    for (int r = 0; r < kMaxR; ++r)
+      for (int x = 0; x < 2; ++x)
+        if (int rc = cuda_check(cudaFuncSetAttribute(table[r][x], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                                "cudaFuncSetAttribute(sot_pair_kernel)")) return rc;
     if (dev < 64) attr_set[dev] = true;
   }
   if (smem > 200 * 1024) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: n_eval too large for shared memory");
