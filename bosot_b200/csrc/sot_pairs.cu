@@ -24,11 +24,10 @@
 
 namespace bosot {
 
-constexpr int kPairWarps = 4;
-constexpr int kPairThreads = kPairWarps * 32;
-constexpr int kChunk = 16;  // trees scanned per warp pass: half the lanes idle in phase A (5% of the
-                            // work) in exchange for half the shared memory => twice the resident warps
-constexpr int kMaxR = 8;    // evaluated trees per lane per register tile (E <= 256 in one pass, else tiles of 256)
+constexpr int kMaxPairWarps = 16;
+constexpr int kMaxChunk = 16;  // trees scanned per warp pass: half the lanes idle in phase A (5% of the work)
+                               // in exchange for half the shared memory => twice the resident warps
+constexpr int kMaxR = 8;       // evaluated trees per lane per register tile (E <= 256 in one pass, else tiles of 256)
 
 __constant__ double c_recip[64];  // 1/T for T = 1..63 ([0] unused)
 
@@ -44,12 +43,58 @@ struct PairParams {
   double* Df;
   int64_t ld;
   int32_t* status;
+  int chunk;  // trees per warp pass (1..kMaxChunk)
 };
 
-// per-warp shared memory: kChunk tree records, candidate dim-wise vector, accumulators, symbol counts
-__host__ __device__ inline size_t pair_warp_smem(int e_pad) {
-  return (size_t)kChunk * kRecBytes + sizeof(double) * BOSOT_MAX_DIM_COLS + sizeof(uint32_t) * (size_t)e_pad +
+// per-warp shared memory: `chunk` tree records, candidate dim-wise vector, accumulators, symbol counts
+__host__ __device__ inline size_t pair_warp_smem(int e_pad, int chunk) {
+  return (size_t)chunk * kRecBytes + sizeof(double) * BOSOT_MAX_DIM_COLS + sizeof(uint32_t) * (size_t)e_pad +
          sizeof(uint32_t) * (BOSOT_MAX_SYMBOLS + BOSOT_MAX_BLOCKS);
+}
+
+// CTA-wide staged copy of the evaluated set's dense tables (section sizes are multiples of 16 bytes)
+struct StageLayout {
+  size_t off_dimT, off_rsub, off_rpath, off_symT, off_nn, off_nl, total;
+  uint32_t b_dimT, b_r, b_symT, b_n;
+};
+__host__ __device__ inline StageLayout stage_layout(int e_pad, int n_dim_cols, int n_symbols) {
+  StageLayout S;
+  S.b_dimT = (uint32_t)(sizeof(double) * (size_t)n_dim_cols * e_pad);
+  S.b_r = (uint32_t)(sizeof(double) * (size_t)e_pad);
+  S.b_symT = (uint32_t)((size_t)n_symbols * e_pad);
+  S.b_n = (uint32_t)e_pad;
+  size_t o = 16;  // mbarrier
+  S.off_dimT = o;  o += S.b_dimT;
+  S.off_rsub = o;  o += S.b_r;
+  S.off_rpath = o; o += S.b_r;
+  S.off_symT = o;  o += S.b_symT;
+  S.off_nn = o;    o += S.b_n;
+  S.off_nl = o;    o += S.b_n;
+  S.total = align16(o);
+  return S;
+}
+
+// ---- TMA bulk copy (global -> shared) completing on an mbarrier -----------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WAIT_%=;\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 // exp(x) for x <= 0 (the Gram argument -d / l^2): Cody-Waite reduction by ln 2, degree-13 Taylor
@@ -80,17 +125,41 @@ __device__ __forceinline__ double exp_nonpos(double x) {
 }
 
 template <int R, bool kExtra>  // R: evaluated trees per lane per tile; kExtra: also write D and/or Df
-__global__ void __launch_bounds__(kPairThreads)
+__global__ void __launch_bounds__(kMaxPairWarps * 32)
 sot_pair_kernel(PairParams p, bosot_grammar g) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const int n_warps = blockDim.x >> 5;
   const int E = p.L.n_eval;
   const int e_pad = p.L.e_pad;
+  const int F = g.n_dim_cols;
   const unsigned full = 0xffffffffu;
 
-  uint8_t* wbase = smem + (size_t)warp * pair_warp_smem(e_pad);
-  uint8_t* recs = wbase;                                                   // kChunk * 424 B
+  // ---- stage the evaluated set's dense tables once per (persistent) CTA: TMA bulk copies -> mbarrier
+  const StageLayout S = stage_layout(e_pad, F, g.n_symbols);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, S.b_dimT + 2 * S.b_r + S.b_symT + 2 * S.b_n);
+    tma_bulk_g2s(smem + S.off_dimT, p.blob + p.L.off_dimT, S.b_dimT, bar);
+    tma_bulk_g2s(smem + S.off_rsub, p.blob + p.L.off_rsub, S.b_r, bar);
+    tma_bulk_g2s(smem + S.off_rpath, p.blob + p.L.off_rpath, S.b_r, bar);
+    tma_bulk_g2s(smem + S.off_symT, p.blob + p.L.off_symT, S.b_symT, bar);
+    tma_bulk_g2s(smem + S.off_nn, p.blob + p.L.off_nnodes, S.b_n, bar);
+    tma_bulk_g2s(smem + S.off_nl, p.blob + p.L.off_nleaves, S.b_n, bar);
+  }
+  const double* dimT = reinterpret_cast<const double*>(smem + S.off_dimT);
+  const double* e_rsub = reinterpret_cast<const double*>(smem + S.off_rsub);
+  const double* e_rpath = reinterpret_cast<const double*>(smem + S.off_rpath);
+  const uint8_t* symT = smem + S.off_symT;
+  const uint8_t* e_nn = smem + S.off_nn;
+  const uint8_t* e_nl = smem + S.off_nl;
+
+  const int kChunk = p.chunk;
+  uint8_t* wbase = smem + S.total + (size_t)warp * pair_warp_smem(e_pad, kChunk);
+  uint8_t* recs = wbase;                                                   // chunk * 424 B
   double* avec = reinterpret_cast<double*>(wbase + kChunk * kRecBytes);    // candidate DIM_WISE vector
   uint32_t* acc = reinterpret_cast<uint32_t*>(avec + BOSOT_MAX_DIM_COLS);  // M_sub(ops) | M_path << 16 per e
   uint32_t* scnt = acc + e_pad;                                            // leaf count per symbol
@@ -99,19 +168,13 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(p.blob + p.L.off_keys);
   const uint2* range = reinterpret_cast<const uint2*>(p.blob + p.L.off_range);
   const uint32_t* post = reinterpret_cast<const uint32_t*>(p.blob + p.L.off_post);
-  const uint8_t* e_nn = p.blob + p.L.off_nnodes;
-  const uint8_t* e_nl = p.blob + p.L.off_nleaves;
-  const double* e_rsub = reinterpret_cast<const double*>(p.blob + p.L.off_rsub);
-  const double* e_rpath = reinterpret_cast<const double*>(p.blob + p.L.off_rpath);
-  const uint8_t* symT = p.blob + p.L.off_symT;
-  const double* dimT = reinterpret_cast<const double*>(p.blob + p.L.off_dimT);
   const int hash_cap = p.L.hash_cap;
-  const int F = g.n_dim_cols;
   const size_t plane = (size_t)p.n_cand * p.ld;
+  bool staged = false;
 
   const int64_t n_chunks = (p.n_cand + kChunk - 1) / kChunk;
-  for (int64_t chunk = (int64_t)blockIdx.x * kPairWarps + warp; chunk < n_chunks;
-       chunk += (int64_t)gridDim.x * kPairWarps) {
+  for (int64_t chunk = (int64_t)blockIdx.x * n_warps + warp; chunk < n_chunks;
+       chunk += (int64_t)gridDim.x * n_warps) {
     const int64_t c0 = chunk * kChunk;
     const int in_chunk = (int)min((int64_t)kChunk, p.n_cand - c0);
 
@@ -129,6 +192,11 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
       if (p.status) p.status[c0 + lane] = st;
     }
     __syncwarp();
+
+    if (!staged) {  // the table copy has been overlapping the first scan
+      mbar_wait(bar, 0);
+      staged = true;
+    }
 
     // ---- phases B + C, one tree at a time, whole warp cooperating
     for (int j = 0; j < in_chunk; ++j) {
@@ -227,7 +295,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
           const uint8_t* nnp = e_nn + eb;
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            tbs[r] = __ldg(nnp + 32 * r);
+            tbs[r] = nnp[32 * r];
             msub[r] = 0u;
             ddim[r] = 0.0;
           }
@@ -240,7 +308,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
           const uint32_t ca = __shfl_sync(full, cnt_sym, src);
           const uint8_t* col = symT + s * (uint32_t)e_pad + eb;
 #pragma unroll
-          for (int r = 0; r < R; ++r) msub[r] += min(ca * tbs[r], (uint32_t)__ldg(col + 32 * r) * (uint32_t)nn);
+          for (int r = 0; r < R; ++r) msub[r] += min(ca * tbs[r], (uint32_t)col[32 * r] * (uint32_t)nn);
         }
         // DIM_WISE: dense L1 over the d * (kinds + 1) columns, column-outer so the candidate value is read once
         {
@@ -248,7 +316,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
           for (int c = 0; c < F; ++c, col += e_pad) {
             const double a = avec[c];
 #pragma unroll
-            for (int r = 0; r < R; ++r) ddim[r] += fabs(a - __ldg(col + 32 * r));
+            for (int r = 0; r < R; ++r) ddim[r] += fabs(a - col[32 * r]);
           }
         }
 #pragma unroll
@@ -257,12 +325,12 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
           if (e < E) {
             const uint32_t a = acc[e];
             const uint32_t m_sub = msub[r] + (a & 0xffffu), m_path = a >> 16;
-            const uint32_t tb_path = __ldg(&e_nl[e]);
+            const uint32_t tb_path = e_nl[e];
             // 2 - 2*M/(Ta*Tb); exactly 0 when the histograms coincide; (1/Ta)*(1/Tb) first keeps D(a,b) == D(b,a) bitwise
             const double d_sub = (m_sub == (uint32_t)nn * tbs[r])
-                                     ? 0.0 : fma(-2.0, (double)m_sub * (rTa_sub * __ldg(&e_rsub[e])), 2.0);
+                                     ? 0.0 : fma(-2.0, (double)m_sub * (rTa_sub * e_rsub[e]), 2.0);
             const double d_path = (m_path == (uint32_t)nl * tb_path)
-                                      ? 0.0 : fma(-2.0, (double)m_path * (rTa_path * __ldg(&e_rpath[e])), 2.0);
+                                      ? 0.0 : fma(-2.0, (double)m_path * (rTa_path * e_rpath[e]), 2.0);
             // sum_f w_f * D_f in feature_type_list order (kernel_kernel_grammar_tree.py:159-161)
             const double d = __dadd_rn(__dadd_rn(__dmul_rn(p.w_dim, ddim[r]), __dmul_rn(p.w_path, d_path)),
                                        __dmul_rn(p.w_sub, d_sub));
@@ -277,6 +345,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
       __syncwarp();
     }
   }
+  if (!staged) mbar_wait(bar, 0);  // never leave a bulk copy in flight behind an exiting CTA
 }
 
 static bool g_recip_ready[64] = {false};  // per device
@@ -320,11 +389,28 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   p.ld = ld;
   p.status = d_status;
 
-  const size_t smem = kPairWarps * pair_warp_smem(p.L.e_pad);
-  static bool attr_set[64] = {false};
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   if (int rc = cuda_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return rc;
+
+  // Shape the launch to the pool: big pools run one persistent 16-warp CTA per SM on 16-tree chunks;
+  // small pools (e.g. 10k candidates) shrink the chunk and the CTA so every SM still gets warps.
+  const int64_t target_warps = (int64_t)sms * kMaxPairWarps;
+  int chunk = kMaxChunk;
+  while (chunk > 1 && (n_cand + chunk - 1) / chunk < target_warps) chunk >>= 1;
+  const int64_t n_chunks = (n_cand + chunk - 1) / chunk;
+  int warps = kMaxPairWarps;
+  while (warps > 1 && (n_chunks + warps - 1) / warps < sms) warps >>= 1;
+  p.chunk = chunk;
+  const StageLayout S = stage_layout(p.L.e_pad, grammar->n_dim_cols, grammar->n_symbols);
+  size_t smem = S.total + (size_t)warps * pair_warp_smem(p.L.e_pad, chunk);
+  const size_t smem_cap = 200 * 1024;
+  while (smem > smem_cap && warps > 1) {
+    warps >>= 1;
+    smem = S.total + (size_t)warps * pair_warp_smem(p.L.e_pad, chunk);
+  }
+  if (smem > smem_cap) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: n_eval too large for shared memory");
+
   const bool extra = d_D != nullptr || d_Df != nullptr;
   const int rounds = p.L.e_pad / 32;
   const int R = rounds < kMaxR ? rounds : kMaxR;
@@ -335,23 +421,24 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
       {sot_pair_kernel<5, false>, sot_pair_kernel<5, true>}, {sot_pair_kernel<6, false>, sot_pair_kernel<6, true>},
       {sot_pair_kernel<7, false>, sot_pair_kernel<7, true>}, {sot_pair_kernel<8, false>, sot_pair_kernel<8, true>}};
   KernelFn kernel = table[R - 1][extra ? 1 : 0];
+  static bool attr_set[64] = {false};
   if (!(dev < 64 && attr_set[dev])) {
     for (int r = 0; r < kMaxR; ++r)
       for (int x = 0; x < 2; ++x)
-        if (int rc = cuda_check(cudaFuncSetAttribute(table[r][x], cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+        if (int rc = cuda_check(cudaFuncSetAttribute(table[r][x], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
                                 "cudaFuncSetAttribute(sot_pair_kernel)")) return rc;
     if (dev < 64) attr_set[dev] = true;
   }
-  if (smem > 200 * 1024) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: n_eval too large for shared memory");
   int per_sm = 1;
-  if (int rc = cuda_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPairThreads, smem),
+  if (int rc = cuda_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem),
                           "cudaOccupancyMaxActiveBlocksPerMultiprocessor")) return rc;
   if (per_sm < 1) per_sm = 1;
-  // grid: a whole number of waves (SMs x resident CTAs), persistent loop over 32-tree chunks
-  const int64_t want = ((n_cand + kChunk - 1) / kChunk + kPairWarps - 1) / kPairWarps;
+  // at most kMaxPairWarps resident warps per SM (leaves the rest of the unified L1 to the postings / hash table)
+  if (per_sm * warps > kMaxPairWarps) per_sm = kMaxPairWarps / warps;
+  const int64_t want = (n_chunks + warps - 1) / warps;
   const int64_t wave = (int64_t)sms * per_sm;
   const int64_t grid = want < wave ? want : wave;
-  kernel<<<(unsigned)grid, kPairThreads, smem, stream>>>(p, *grammar);
+  kernel<<<(unsigned)grid, warps * 32, smem, stream>>>(p, *grammar);
   return after_launch("sot_pair_kernel");
 }
 
