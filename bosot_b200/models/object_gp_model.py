@@ -1,0 +1,309 @@
+"""GP over kernel space: drop-in for bosot/models/object_gp_model.py (+ the parts of
+bosot/models/gp_model.py and object_gpr.py it inherits: infer / optimize / pertube_parameters /
+predictive_dist ...), with GPflow replaced by:
+
+  * the CUDA hot path (``bosot_b200.sot``) for everything per candidate / per pair, and
+  * a small fp64 torch routine on the same device for the E x E marginal likelihood of the
+    hyper-parameter fit, driven by SciPy L-BFGS-B exactly like
+    ``gpflow.optimizers.Scipy`` drives TF (bosot/models/gp_model.py:162-193).
+
+Parameters live in GPflow's unconstrained space during the fit: ``alphas`` through a sigmoid,
+``lengthscale`` / ``variance`` through softplus (kernel_kernel_grammar_tree.py:103-107), the
+likelihood variance through softplus shifted by GPflow's 1e-6 lower bound, the constant mean as is.
+The random perturbation (gp_model.py:263-282) walks the trainable variables in GPflow's order
+(kernel.alphas, kernel.lengthscale, kernel.variance, likelihood.variance, mean_function.c) and
+consumes the global ``np.random`` stream the same way.
+"""
+from __future__ import annotations
+
+import copy
+import logging
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+from scipy.optimize import minimize
+from scipy.stats import norm
+
+from .. import _lib, sot
+from ..kernels.base_object_kernel import BaseObjectKernel
+from ..kernels.kernel_kernel_grammar_tree import _DEVICE_ORDER, FlatTrees, Parameter
+from .gp_model import PredictionQuantity
+from .object_mean_functions import MeanFunction, Zero
+
+logger = logging.getLogger(__name__)
+
+LIKELIHOOD_VARIANCE_LOWER_BOUND = 1e-6  # gpflow.likelihoods.Gaussian DEFAULT_VARIANCE_LOWER_BOUND
+
+
+def _softplus_inv(y: np.ndarray) -> np.ndarray:
+    y = np.asarray(y, dtype=np.float64)
+    return np.where(y > 30.0, y, np.log(np.expm1(np.minimum(y, 30.0))))
+
+
+def _softplus(x: np.ndarray) -> np.ndarray:
+    x = np.asarray(x, dtype=np.float64)
+    return np.where(x > 30.0, x, np.log1p(np.exp(np.minimum(x, 30.0))))
+
+
+class ObjectGpModel:
+    def __init__(
+        self,
+        kernel: BaseObjectKernel,
+        observation_noise: float,
+        optimize_hps: bool,
+        train_likelihood_variance: bool,
+        pertube_parameters_at_start=False,
+        perform_multi_start_optimization=False,
+        set_prior_on_observation_noise=False,
+        n_starts_for_multistart_opt: int = 5,
+        expected_observation_noise: float = 0.1,
+        prediction_quantity: PredictionQuantity = PredictionQuantity.PREDICT_Y,
+        **kwargs
+    ):
+        assert isinstance(kernel, BaseObjectKernel)
+        self.kernel = copy.deepcopy(kernel)  # the model owns its kernel, like gp_model.py:72
+        self._initial_kernel_values = [np.array(p.numpy(), copy=True) for p in self._kernel_parameters()]
+        self.observation_noise = observation_noise
+        self.optimize_hps = optimize_hps
+        self.train_likelihood_variance = train_likelihood_variance
+        self.pertube_parameters_at_start = pertube_parameters_at_start
+        self.perform_multi_start_optimization = perform_multi_start_optimization
+        self.n_starts_for_multistart_opt = n_starts_for_multistart_opt
+        self.pertubation_for_multistart_opt = 0.5
+        self.set_prior_on_observation_noise = set_prior_on_observation_noise
+        self.expected_observation_noise = expected_observation_noise
+        self.prediction_quantity = prediction_quantity
+        self.use_mean_function = False
+        self.mean_function: MeanFunction = Zero()
+        self.model = None  # the "built model": evaluated-set state on the device
+        self.likelihood_variance = Parameter(np.power(observation_noise, 2.0), trainable=train_likelihood_variance)
+        self._engine = None
+        self.print_summaries = True
+
+    # ------------------------------------------------------------------ small helpers
+    def _kernel_parameters(self) -> List[Parameter]:
+        return [self.kernel.alphas, self.kernel.lengthscale, self.kernel.variance]
+
+    def set_mean_function(self, mean_function: MeanFunction):
+        self.use_mean_function = True
+        self.mean_function = mean_function
+
+    def set_number_of_restarts(self, n_starts: int):
+        self.n_starts_for_multistart_opt = n_starts
+
+    def deactivate_summary_printing(self):
+        self.print_summaries = False
+
+    def transform_input(self, x):
+        return self.kernel.transform_X(x)
+
+    def reset_model(self):
+        """Kernel parameters back to their initial values, built model dropped (gp_model.py:92-98)."""
+        if self.model is not None:
+            for p, v in zip(self._kernel_parameters(), self._initial_kernel_values):
+                p.assign(v)
+            self.model = None
+            self._engine = None
+
+    # ---------------------------------------------------------------------- build / infer
+    def build_model(self, x_data, y_data: np.ndarray):
+        """object_gp_model.py:64-76: fixes the data; here that also means the flat encoding of the
+        evaluated kernels, their inverted index, and the three E x E per-feature distance matrices
+        (constants with respect to every hyper-parameter)."""
+        flat = self.kernel.flatten(x_data)
+        y = np.asarray(y_data, dtype=np.float64).reshape(-1, 1)
+        assert len(flat) == y.shape[0]
+        state = sot.EvalState(flat.trees, flat.grammar)
+        Df = sot.sot_pairs(flat.trees, state, (1.0, 1.0, 1.0), 1.0, 1.0, want=("Df",))["Df"]
+        self.likelihood_variance = Parameter(np.power(self.observation_noise, 2.0), trainable=self.train_likelihood_variance)
+        self.model = dict(flat=flat, state=state, Df=Df, y=torch.from_numpy(y[:, 0].copy()).to(flat.trees.device))
+        self._engine = None
+
+    def infer(self, x_data, y_data: np.ndarray):
+        x_data = self.transform_input(x_data)
+        self.build_model(x_data, y_data)
+        if self.optimize_hps:
+            if self.perform_multi_start_optimization:
+                self.multi_start_optimization(self.n_starts_for_multistart_opt, self.pertubation_for_multistart_opt)
+            else:
+                self.optimize(self.pertube_parameters_at_start)
+
+    # ------------------------------------------------- hyper-parameter fit (ML-II, L-BFGS-B)
+    def _trainables(self):
+        """(parameter, to_unconstrained, from_unconstrained) in GPflow's variable order."""
+        sig_inv = lambda a: np.log(a) - np.log1p(-a)  # noqa: E731
+        sig = lambda u: 1.0 / (1.0 + np.exp(-u))  # noqa: E731
+        out = []
+        k = self.kernel
+        if k.alphas.trainable:
+            out.append((k.alphas, sig_inv, sig))
+        if k.lengthscale.trainable:
+            out.append((k.lengthscale, _softplus_inv, _softplus))
+        if k.variance.trainable:
+            out.append((k.variance, _softplus_inv, _softplus))
+        if self.likelihood_variance.trainable:
+            lo = LIKELIHOOD_VARIANCE_LOWER_BOUND
+            out.append((self.likelihood_variance, lambda v: _softplus_inv(v - lo), lambda u: _softplus(u) + lo))
+        c = getattr(self.mean_function, "c", None)
+        if self.use_mean_function and isinstance(c, Parameter) and c.trainable:
+            out.append((c, lambda v: np.asarray(v, dtype=np.float64), lambda u: np.asarray(u, dtype=np.float64)))
+        return out
+
+    def pertube_parameters(self, factor_bound: float):
+        """gp_model.py:263-282."""
+        for p, v in zip(self._kernel_parameters(), self._initial_kernel_values):
+            p.assign(v)
+        if self.train_likelihood_variance:
+            self.likelihood_variance.assign(np.power(self.observation_noise, 2.0))
+        for p, to_u, from_u in self._trainables():
+            u = to_u(p.numpy())
+            factor = 1 + np.random.uniform(-1 * factor_bound, factor_bound, size=u.shape)
+            if np.isclose(u, 0.0, rtol=1e-07, atol=1e-09).all():
+                new_u = (u + np.random.normal(0, 0.05, size=u.shape)) * factor
+            else:
+                new_u = u * factor
+            p.assign(from_u(new_u))
+
+    def _loss_and_grad(self, theta: np.ndarray, layout) -> Tuple[float, np.ndarray]:
+        """Negative log marginal likelihood of GPR (+ the exponential prior on the noise when asked)
+        and its gradient in unconstrained space: torch fp64 autograd on the device holding D_f."""
+        dev = self.model["Df"].device
+        t = torch.tensor(theta, dtype=torch.float64, device=dev, requires_grad=True)
+        vals = {}
+        pos = 0
+        for name, n in layout:
+            vals[name] = t[pos : pos + n]
+            pos += n
+        k = self.kernel
+        as_t = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float64), device=dev)  # noqa: E731
+        alphas = torch.sigmoid(vals["alphas"]) if "alphas" in vals else as_t(k.alphas.numpy())
+        ls = torch.nn.functional.softplus(vals["lengthscale"])[0] if "lengthscale" in vals else as_t(k.lengthscale.numpy())
+        var = torch.nn.functional.softplus(vals["variance"])[0] if "variance" in vals else as_t(k.variance.numpy())
+        if "noise" in vals:
+            noise = torch.nn.functional.softplus(vals["noise"])[0] + LIKELIHOOD_VARIANCE_LOWER_BOUND
+        else:
+            noise = as_t(self.likelihood_variance.numpy())
+        c = vals["c"][0] if "c" in vals else as_t(self.mean_function.value())
+        w3 = torch.zeros(3, dtype=torch.float64, device=dev)
+        w = alphas / alphas.sum()
+        idx = torch.tensor([_DEVICE_ORDER.index(f) for f in k.feature_type_list], device=dev)
+        w3 = w3.index_add(0, idx, w)
+        D = (w3[:, None, None] * self.model["Df"]).sum(0)
+        E = D.shape[0]
+        Kmat = var * torch.exp(-D / (ls * ls)) + noise * torch.eye(E, dtype=torch.float64, device=dev)
+        L = torch.linalg.cholesky(Kmat)
+        err = (self.model["y"] - c).reshape(E, 1)
+        a = torch.linalg.solve_triangular(L, err, upper=False)
+        lml = -0.5 * (a * a).sum() - torch.log(torch.diagonal(L)).sum() - 0.5 * E * np.log(2 * np.pi)
+        loss = -lml
+        if self.set_prior_on_observation_noise:  # tfd.Exponential(rate) log-density on the constrained value
+            rate = 1.0 / np.power(self.expected_observation_noise, 2.0)
+            loss = loss - (np.log(rate) - rate * noise)
+        (g,) = torch.autograd.grad(loss, t, allow_unused=True)
+        return float(loss), (g.cpu().numpy() if g is not None else np.zeros_like(theta))
+
+    def training_loss(self) -> float:
+        layout, theta, _ = self._pack()
+        return self._loss_and_grad(theta, layout)[0]
+
+    def _pack(self):
+        names = {id(self.kernel.alphas): "alphas", id(self.kernel.lengthscale): "lengthscale", id(self.kernel.variance): "variance",
+                 id(self.likelihood_variance): "noise"}
+        layout, chunks, items = [], [], self._trainables()
+        for p, to_u, _ in items:
+            u = np.atleast_1d(to_u(p.numpy())).astype(np.float64)
+            layout.append((names.get(id(p), "c"), len(u)))
+            chunks.append(u)
+        return layout, (np.concatenate(chunks) if chunks else np.zeros(0)), items
+
+    def _unpack(self, theta, items):
+        pos = 0
+        for p, _, from_u in items:
+            n = int(np.atleast_1d(p.numpy()).size)
+            p.assign(from_u(theta[pos : pos + n]))
+            pos += n
+
+    def optimize(self, pertube_initial_parameters: bool, pertubation_factor=0.2):
+        """gp_model.py:162-193: L-BFGS-B until SciPy reports success; any failure (e.g. Cholesky of a
+        non-PD matrix) or non-convergence re-perturbs and retries."""
+        if pertube_initial_parameters:
+            self.pertube_parameters(pertubation_factor)
+        while True:
+            success = False
+            try:
+                layout, theta0, items = self._pack()
+                if len(theta0) == 0:
+                    return
+                res = minimize(lambda th: self._loss_and_grad(th, layout), theta0, jac=True, method="L-BFGS-B")
+                self._unpack(res.x, items)
+                success = bool(res.success)
+            except Exception:  # noqa: BLE001 -- mirrors the reference's bare except
+                logger.error("Error in optimization - try again")
+                self.pertube_parameters(pertubation_factor)
+            if success:
+                self._engine = None
+                return
+            logger.warning("Not converged - try again")
+            self.pertube_parameters(pertubation_factor)
+
+    def multi_start_optimization(self, n_starts: int, pertubation_factor: float):
+        """gp_model.py:201-245: best of n_starts perturbed fits by final loss."""
+        if self.pertube_parameters_at_start:
+            self.pertube_parameters(0.1)
+        best = None
+        for i in range(n_starts):
+            logger.info("Optimization repeat %d/%d", i + 1, n_starts)
+            self.optimize(True, pertubation_factor)
+            loss = self.training_loss()
+            snapshot = [np.array(p.numpy(), copy=True) for p, _, _ in self._trainables()]
+            if best is None or loss < best[0]:
+                best = (loss, snapshot)
+        for (p, _, _), v in zip(self._trainables(), best[1]):
+            p.assign(np.maximum(v, 1.000001e-06) if p is self.likelihood_variance else v)
+        self._engine = None
+
+    def estimate_model_evidence(self, x_data=None, y_data=None) -> float:
+        if self.model is None and x_data is not None and y_data is not None:
+            self.infer(x_data, y_data)
+        saved, self.set_prior_on_observation_noise = self.set_prior_on_observation_noise, False
+        try:
+            return -self.training_loss()
+        finally:
+            self.set_prior_on_observation_noise = saved
+
+    # -------------------------------------------------------------------------- prediction
+    def engine(self, acq_kind: int = _lib.ACQ_NONE, xi: float = 0.01, ucb_beta: float = 3.0) -> sot.AcquisitionEngine:
+        """Evaluated-set state + Cholesky for the current hyper-parameters (cached until they change)."""
+        key = (acq_kind, xi, ucb_beta, tuple(self.kernel.device_weights()), float(self.kernel.variance), float(self.kernel.lengthscale),
+               float(self.likelihood_variance), self.mean_function.value())
+        if self._engine is None or self._engine[0] != key:
+            m = self.model
+            eng = sot.AcquisitionEngine(
+                m["flat"].trees, m["y"], m["flat"].grammar, self.kernel.device_weights(), float(self.kernel.variance),
+                float(self.kernel.lengthscale), float(self.likelihood_variance), self.mean_function.value(),
+                acq_kind=acq_kind, xi=xi, ucb_beta=ucb_beta, state=m["state"],
+            )
+            self._engine = (key, eng)
+        return self._engine[1]
+
+    def _posterior(self, x_test):
+        flat = self.kernel.flatten(self.transform_input(x_test))
+        mu, sigma, _ = self.engine().acquire_device(flat.trees)
+        return mu, sigma
+
+    def predictive_dist(self, x_test) -> Tuple[np.ndarray, np.ndarray]:
+        """(mu[N], sigma[N]) numpy, like gp_model.py:290-306; PREDICT_Y adds the noise variance."""
+        mu, sigma = self._posterior(x_test)
+        if self.prediction_quantity == PredictionQuantity.PREDICT_Y:
+            sigma = torch.sqrt(sigma * sigma + float(self.likelihood_variance))
+        return np.squeeze(mu.cpu().numpy()), np.squeeze(sigma.cpu().numpy())
+
+    def predictive_log_likelihood(self, x_test, y_test: np.ndarray) -> np.ndarray:
+        mu, sigma = self._posterior(x_test)
+        sig_y = torch.sqrt(sigma * sigma + float(self.likelihood_variance)).cpu().numpy()
+        return norm.logpdf(np.squeeze(y_test), np.squeeze(mu.cpu().numpy()), np.squeeze(sig_y))
+
+    def entropy_predictive_dist(self, x_test) -> np.ndarray:
+        _, sigma = self.predictive_dist(x_test)
+        return (0.5 * np.log(2 * np.pi * np.e * np.power(sigma, 2.0))).reshape(-1, 1)

@@ -1,0 +1,202 @@
+"""GPU: the reference-facing Python API (kernel-kernel class, GP over kernel space, BO loop) against
+the golden fixtures and the CPU oracle.  Reads like the reference's call sites:
+``kernel(X, X2)``, ``model.infer(x, y)``, ``model.predictive_dist(x)``, ``bo.acquisition_function(x)``."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from bosot_b200.bayesian_optimization.bayesian_optimizer_objects import BayesianOptimizerObjects  # noqa: E402
+from bosot_b200.bayesian_optimization.enums import AcquisitionFunctionType  # noqa: E402
+from bosot_b200.configs.bayesian_optimization.bayesian_optimizer_objects_configs import (  # noqa: E402
+    ObjectBOExpectedImprovementEAConfig,
+    ObjectBOGPUCBConfig,
+)
+from bosot_b200.configs.kernels.grammar_tree_kernel_kernel_configs import OTWeightedDimsExtendedGrammarKernelConfig  # noqa: E402
+from bosot_b200.configs.kernels.kernel_grammar_generators.generator_configs import CKSHighDimGeneratorConfig, CKSWithRQGeneratorConfig  # noqa: E402
+from bosot_b200.configs.models.object_gp_model_config import BasicObjectGPModelConfig  # noqa: E402
+from bosot_b200.kernels.kernel_factory import KernelFactory  # noqa: E402
+from bosot_b200.kernels.kernel_grammar.generator_factory import GeneratorFactory  # noqa: E402
+from bosot_b200.kernels.kernel_kernel_grammar_tree import FeatureType, OptimalTransportKernelKernel  # noqa: E402
+from bosot_b200.models.gp_model import PredictionQuantity  # noqa: E402
+from bosot_b200.models.model_factory import ModelFactory  # noqa: E402
+from bosot_b200.models.object_mean_functions import ObjectConstant  # noqa: E402
+from bosot_b200.oracles.structural_oracle import StructuralOracle  # noqa: E402
+from oracle import ref_numpy as rn  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _expressions(names, generator_name, d):
+    """Name strings -> expression objects of the mirror API (what a user of the reference holds)."""
+    from bosot_b200.kernels.kernel_grammar.kernel_grammar import (
+        ElementaryKernelGrammarExpression, KernelGrammarExpression, KernelGrammarOperator, SymbolicKernel)
+
+    def build(t):
+        if isinstance(t, str):
+            e = ElementaryKernelGrammarExpression(SymbolicKernel(t, d))
+        else:
+            e = KernelGrammarExpression(build(t[1]), build(t[2]), KernelGrammarOperator[t[0]])
+        e.set_generator_name(generator_name)
+        return e
+
+    return [build(rn.parse_name(str(s))) for s in names]
+
+
+def _kernel(g, hyper):
+    k = KernelFactory.build(OTWeightedDimsExtendedGrammarKernelConfig(input_dimension=int(g["input_dimension"])))
+    assert isinstance(k, OptimalTransportKernelKernel)
+    k.alphas.assign(hyper.alphas)
+    k.lengthscale.assign(hyper.lengthscale)
+    k.variance.assign(hyper.variance)
+    return k
+
+
+def test_kernel_object_api(golden):
+    gen, d = str(golden["generator_name"]), int(golden["input_dimension"])
+    h = rn.Hyper(**getattr(rn, str(golden["hyper_name"])))
+    xe, xc = _expressions(golden["eval_names"], gen, d), _expressions(golden["cand_names"], gen, d)
+    k = _kernel(golden, h)
+    np.testing.assert_allclose(k(xe, xc).cpu().numpy(), golden["K_eval_cand"], rtol=1e-12)       # kernel(X_train, X_new)
+    np.testing.assert_allclose(k(xe).cpu().numpy(), golden["K_eval_eval"], rtol=1e-12)           # kernel(X_train)
+    assert np.array_equal(k(xc, full_cov=False).cpu().numpy(), np.full(len(xc), h.variance))     # kernel(X_new, full_cov=False)
+    with pytest.raises(ValueError):
+        k(xe, xc, full_cov=False)                                                                # base_object_kernel.py:37
+    np.testing.assert_allclose(k.get_distance_matrix(xe, xc).cpu().numpy(), golden["d_eval_cand"], atol=1e-12)
+    # the reference's own dense-matrix route, through the mirrored methods
+    for ft, ref in ((FeatureType.DIM_WISE_WEIGHTED_ELEMENTARY_COUNT, rn.DIM_WISE), (FeatureType.REDUCED_ELEMENTARY_PATHS, rn.PATHS), (FeatureType.SUBTREES, rn.SUBTREES)):
+        de, dc = k.internal_transform_X(xe, ft), k.internal_transform_X(xc, ft)
+        index = k.create_hash_array_mapping(de + dc)
+        assert np.array_equal(k.feature_matrix(de, index, k.normalize_features(ft)), golden["F_eval_joint_" + ref])
+        assert np.array_equal(k.feature_matrix(dc, index, k.normalize_features(ft)), golden["F_cand_joint_" + ref])
+
+
+def test_object_gp_model_and_acquisition(golden):
+    gen, d = str(golden["generator_name"]), int(golden["input_dimension"])
+    h = rn.Hyper(**getattr(rn, str(golden["hyper_name"])))
+    xe, xc = _expressions(golden["eval_names"], gen, d), _expressions(golden["cand_names"], gen, d)
+    cfg = BasicObjectGPModelConfig(kernel_config=OTWeightedDimsExtendedGrammarKernelConfig(input_dimension=d), optimize_hps=False,
+                                   observation_noise=float(np.sqrt(h.noise_variance)), prediction_quantity=PredictionQuantity.PREDICT_F)
+    model = ModelFactory.build(cfg)
+    model.kernel.alphas.assign(h.alphas)
+    model.kernel.lengthscale.assign(h.lengthscale)
+    model.kernel.variance.assign(h.variance)
+    model.set_mean_function(ObjectConstant(base_c=h.mean_c))
+    model.infer(xe, golden["y"])
+    mu, sigma = model.predictive_dist(xc)
+    assert mu.shape == (len(xc),) and isinstance(mu, np.ndarray)
+    np.testing.assert_allclose(mu, golden["mu"], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(sigma, golden["sigma"], rtol=1e-6, atol=1e-12)
+    for cfg_cls, key in ((ObjectBOExpectedImprovementEAConfig, "ei"), (ObjectBOGPUCBConfig, "ucb")):
+        bo = BayesianOptimizerObjects(**cfg_cls().dict())
+        bo.set_model(model)
+        bo.set_train_set(xe, golden["y"], [0.0] * len(xe))
+        acq = bo.acquisition_function(xc)
+        assert isinstance(acq, np.ndarray) and acq.shape == (len(xc),)
+        np.testing.assert_allclose(acq, golden[key], rtol=1e-6, atol=1e-12)
+    # PREDICT_Y: sigma carries the likelihood variance (gp_model.py:303-304)
+    model.prediction_quantity = PredictionQuantity.PREDICT_Y
+    _, sig_y = model.predictive_dist(xc)
+    np.testing.assert_allclose(sig_y, np.sqrt(golden["sigma"] ** 2 + h.noise_variance), rtol=1e-6)
+    bo = BayesianOptimizerObjects(**ObjectBOExpectedImprovementEAConfig().dict())
+    bo.set_model(model)
+    bo.set_train_set(xe, golden["y"], [0.0] * len(xe))
+    mu_e = golden["mu_eval"]
+    dd = golden["mu"] - np.max(mu_e) - 0.01
+    from scipy.stats import norm
+    np.testing.assert_allclose(bo.acquisition_function(xc), dd * norm.cdf(dd / sig_y) + sig_y * norm.pdf(dd / sig_y), rtol=1e-6, atol=1e-12)
+
+
+def test_marginal_likelihood_and_gradient():
+    gen = GeneratorFactory.build(CKSHighDimGeneratorConfig(input_dimension=3))
+    np.random.seed(5)
+    x = gen.get_dataset_recursivly_generated(30, 1)
+    y = np.random.default_rng(0).standard_normal((30, 1))
+    cfg = BasicObjectGPModelConfig(kernel_config=OTWeightedDimsExtendedGrammarKernelConfig(input_dimension=3), optimize_hps=False,
+                                   prediction_quantity=PredictionQuantity.PREDICT_F)
+    model = ModelFactory.build(cfg)
+    model.set_mean_function(ObjectConstant(base_c=0.2))
+    model.infer(x, y)
+    # value against the NumPy restatement of GPR.log_marginal_likelihood
+    trees = [rn.parse_name(str(e)) for e in x]
+    hyp = rn.Hyper(noise_variance=1e-4, mean_c=0.2)
+    K = rn.K(trees, None, hyp, "CKSHighDimSearchSpace", 3) + 1e-4 * np.eye(30)
+    L = np.linalg.cholesky(K)
+    a = np.linalg.solve(L, y - 0.2)
+    lml = -0.5 * float(a.T @ a) - np.log(np.diag(L)).sum() - 15 * np.log(2 * np.pi)
+    np.testing.assert_allclose(model.estimate_model_evidence(), lml, rtol=1e-9)
+    # analytic (autograd) gradient against central differences in unconstrained space
+    layout, theta, _ = model._pack()
+    assert [n for n, _ in layout] == ["alphas", "lengthscale", "variance", "noise", "c"] and len(theta) == 7
+    f0, g = model._loss_and_grad(theta, layout)
+    for i in range(len(theta)):
+        e = np.zeros_like(theta)
+        e[i] = 1e-6
+        num = (model._loss_and_grad(theta + e, layout)[0] - model._loss_and_grad(theta - e, layout)[0]) / 2e-6
+        np.testing.assert_allclose(g[i], num, rtol=2e-4, atol=1e-6)
+    # the fit lowers the loss and keeps the parameters in their domains
+    model.optimize_hps = True
+    np.random.seed(0)
+    before = model.training_loss()
+    model.optimize(True)
+    assert model.training_loss() < before
+    assert np.all((model.kernel.alphas.numpy() > 0) & (model.kernel.alphas.numpy() < 1))
+    assert float(model.kernel.lengthscale) > 0 and float(model.kernel.variance) > 0 and float(model.likelihood_variance) >= 1e-6
+    model.reset_model()
+    assert np.array_equal(model.kernel.alphas.numpy(), [0.5, 0.5, 0.5]) and model.model is None
+
+
+class _OracleAcquisitionBO(BayesianOptimizerObjects):
+    """Same loop, acquisition_function replaced by the CPU oracle's (reference formulas, NumPy fp64)."""
+
+    def __init__(self, hyper, gen_name, d, **kw):
+        super().__init__(**kw)
+        self._h, self._g, self._d = hyper, gen_name, d
+
+    def update(self, step):
+        from bosot_b200.bayesian_optimization.evolutionary_optimizer_objects import EvolutionaryOptimizerObjects
+
+        opt = EvolutionaryOptimizerObjects(self.population_evolutionary, self.num_offspring_evolutionary, self.candidate_generator)
+        q, _ = opt.maximize(self.acquisition_function, self.n_steps_evolutionary)
+        return q, None
+
+    def acquisition_function(self, x_grid):
+        t = lambda xs: [rn.parse_name(str(x)) for x in xs]  # noqa: E731
+        return rn.acquisition_function(t(self.x_data), self.y_data, t(x_grid), self._h, self._g, self._d)["acq"]
+
+
+def test_bo_loop_makes_the_same_selections_as_the_cpu_path():
+    """Toy run (CKSWithRQ, d = 2, like bosot/examples/bayesian_optimization_kernel_space.py with a
+    deterministic stand-in objective and fixed hyper-parameters): the GPU-backed loop and the loop
+    driven by the CPU oracle's acquisition values must query the same kernels in the same order."""
+    d, space = 2, "CKSWithRQSearchSpace"
+    hyp = rn.Hyper(**rn.H1)
+    bo_cfg = ObjectBOExpectedImprovementEAConfig(n_steps_evolutionary=3, population_evolutionary=50).dict()
+    runs = []
+    for which in ("gpu", "cpu"):
+        gen = GeneratorFactory.build(CKSWithRQGeneratorConfig(input_dimension=d))
+        oracle = StructuralOracle([str(r) for r in gen.search_space.get_root_expressions()], seed=3)
+        if which == "gpu":
+            model = ModelFactory.build(BasicObjectGPModelConfig(
+                kernel_config=OTWeightedDimsExtendedGrammarKernelConfig(input_dimension=d), optimize_hps=False,
+                observation_noise=float(np.sqrt(hyp.noise_variance)), prediction_quantity=PredictionQuantity.PREDICT_F))
+            model.kernel.alphas.assign(hyp.alphas)
+            model.kernel.lengthscale.assign(hyp.lengthscale)
+            model.kernel.variance.assign(hyp.variance)
+            model.set_mean_function(ObjectConstant(base_c=hyp.mean_c))
+            bo = BayesianOptimizerObjects(**bo_cfg)
+            bo.set_model(model)
+        else:
+            bo = _OracleAcquisitionBO(hyp, space, d, **bo_cfg)
+        bo.set_oracle(oracle)
+        bo.set_candidate_generator(gen)
+        np.random.seed(42)
+        bo.sample_train_set(16)
+        metrics, queries, bests, *_ = bo.maximize(5)
+        runs.append(([str(q) for q, _ in queries], [v for _, v in queries], str(bo.get_current_best()), metrics))
+    assert runs[0][0] == runs[1][0], (runs[0][0], runs[1][0])
+    np.testing.assert_allclose(runs[0][1], runs[1][1])
+    assert runs[0][2] == runs[1][2]
+    assert runs[0][3][-1] >= runs[0][3][0] and len(runs[0][3]) == 6
+    assert runs[0][0], "no queries"
+    assert isinstance(AcquisitionFunctionType.EXPECTED_IMPROVEMENT, AcquisitionFunctionType)
