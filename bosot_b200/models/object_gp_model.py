@@ -201,7 +201,7 @@ class ObjectGpModel:
             rate = 1.0 / np.power(self.expected_observation_noise, 2.0)
             loss = loss - (np.log(rate) - rate * noise)
         (g,) = torch.autograd.grad(loss, t, allow_unused=True)
-        return float(loss), (g.cpu().numpy() if g is not None else np.zeros_like(theta))
+        return float(loss.detach()), (g.cpu().numpy() if g is not None else np.zeros_like(theta))
 
     def training_loss(self) -> float:
         layout, theta, _ = self._pack()
