@@ -240,13 +240,16 @@ def main() -> None:
     status = torch.empty(n_local, dtype=torch.int32, device=dev)
     import ctypes as C
 
+    scratch = torch.empty(_lib.load().bosot_sot_pairs_scratch_bytes(n_local), dtype=torch.uint8, device=dev)
+
     lib = _lib.load()
     wd = (C.c_double * 3)(*[float(x) for x in w])
     stream = torch.cuda.current_stream(dev).cuda_stream
 
     def k_pairs():
         _lib.check(lib.bosot_sot_pairs(d_ca.data_ptr(), n_local, C.byref(gram.c_struct), eng.state.blob.data_ptr(), N_EVAL, wd,
-                                       hyp.variance, hyp.lengthscale, Kbuf.data_ptr(), None, None, N_EVAL, status.data_ptr(), stream))
+                                       hyp.variance, hyp.lengthscale, Kbuf.data_ptr(), None, None, N_EVAL, status.data_ptr(),
+                                       scratch.data_ptr(), scratch.numel(), stream))
 
     def k_post():
         _lib.check(lib.bosot_posterior_acq(Kbuf.data_ptr(), n_local, N_EVAL, N_EVAL, eng.Linv.data_ptr(), eng.Linv.shape[1],

@@ -43,15 +43,16 @@ int check_grammar(const bosot_grammar* g) {
 // defined in sot_pairs.cu / posterior.cu
 int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar, const void* d_eval_blob,
                  int n_eval, const double weights[3], double variance, double lengthscale, double* d_K, double* d_D,
-                 double* d_Df, int64_t ld, int32_t* d_status, cudaStream_t stream);
+                 double* d_Df, int64_t ld, int32_t* d_status, void* d_scratch, size_t scratch_bytes, cudaStream_t stream);
+size_t pairs_scratch_bytes(int64_t n_cand);
 int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval, const double* d_Linv, int ldl,
                      const double* d_beta, double mean_c, double variance, int acq_kind, const double* d_current_max,
                      double xi, double ucb_beta, double* d_mu, double* d_sigma, double* d_acq, cudaStream_t stream);
 
-// work buffer of the composed calls:  K*[n_cand][ld] | trees[n_cand][64] | mu | sigma | acq | status
+// work buffer of the composed calls:  K*[n_cand][ld] | trees[n_cand][64] | mu | sigma | acq | status | scan records
 struct WorkLayout {
   int64_t ld;
-  size_t off_K, off_trees, off_mu, off_sigma, off_acq, off_status, total;
+  size_t off_K, off_trees, off_mu, off_sigma, off_acq, off_status, off_recs, total;
 };
 static WorkLayout work_layout(int64_t n_cand, int n_eval) {
   WorkLayout W;
@@ -63,6 +64,7 @@ static WorkLayout work_layout(int64_t n_cand, int n_eval) {
   W.off_sigma = o;  o = align16(o + sizeof(double) * (size_t)n_cand);
   W.off_acq = o;    o = align16(o + sizeof(double) * (size_t)n_cand);
   W.off_status = o; o = align16(o + sizeof(int32_t) * (size_t)n_cand);
+  W.off_recs = o;   o = align16(o + pairs_scratch_bytes(n_cand));
   W.total = o;
   return W;
 }
@@ -104,7 +106,7 @@ extern "C" int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, cons
   int32_t* status = reinterpret_cast<int32_t*>(w + W.off_status);
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = launch_pairs(d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale, K, nullptr,
-                            nullptr, W.ld, status, st)) return rc;
+                            nullptr, W.ld, status, w + W.off_recs, pairs_scratch_bytes(n_cand), st)) return rc;
   return launch_posterior(K, n_cand, W.ld, n_eval, d_Linv, ldl, d_beta, mean_c, variance, acq_kind, d_current_max, xi,
                           ucb_beta, d_mu, d_sigma, d_acq, st);
 }

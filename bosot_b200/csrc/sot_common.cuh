@@ -21,15 +21,17 @@ constexpr int kMaxLeaves = BOSOT_MAX_LEAVES;
 constexpr int kMaxInternal = BOSOT_MAX_INTERNAL;
 constexpr int kPathCodes = BOSOT_PATH_CODES;
 
-// Per-tree working record in shared memory.  Stride 424 B = 8 * 53 (odd multiple of 8):
-// 64-bit accesses of 32 threads working on 32 different trees spread over all banks,
-// and a warp working on ONE tree reads consecutive ids / bytes.
+// Per-tree working record in shared memory (scan phase).  Stride 424 B = 8 * 53 (odd multiple of 8):
+// 64-bit accesses of 32 threads working on 32 different trees spread over all banks.  The first
+// kScanBytes bytes are the compact record that leaves the scan (class ids, meta, leaf symbols, reduced
+// path codes); the rest is scratch of the two passes.
 constexpr int kRecIid = 0;        // uint64 iid[31]   class ids of internal nodes (by reverse pre-order rank)
-constexpr int kRecTok = 248;      // uint8  raw record: n, tokens (64 B)
-constexpr int kRecStack = 312;    // uint8  stack[32] scratch of the two scans
-constexpr int kRecLeafSym = 344;  // uint8  leaf_sym[32]   leaves in pre-order (left to right)
-constexpr int kRecLeafCode = 376; // uint8  leaf_code[32]  reduced path code per leaf
-constexpr int kRecMeta = 408;     // uint8  n_nodes, n_leaves, n_internal, status
+constexpr int kRecMeta = 248;     // uint8  n_nodes, n_leaves, n_internal, status (+4 pad)
+constexpr int kRecLeafSym = 256;  // uint8  leaf_sym[32]   leaves in pre-order (left to right)
+constexpr int kRecLeafCode = 288; // uint8  leaf_code[32]  reduced path code per leaf
+constexpr int kScanBytes = 320;   // compact record = what the pair kernel consumes
+constexpr int kRecTok = 320;      // uint8  raw record: n, tokens (64 B)
+constexpr int kRecStack = 384;    // uint8  stack[32] scratch of the two scans
 constexpr int kRecBytes = 424;
 
 __device__ __forceinline__ uint64_t fmix64(uint64_t x) {

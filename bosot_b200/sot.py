@@ -168,11 +168,12 @@ def sot_pairs(
     if "Df" in want:
         out["Df"] = torch.empty((3, n, E), dtype=torch.float64, device=dev)
     status = torch.empty(n, dtype=torch.int32, device=dev)
+    scratch = torch.empty(max(16, lib.bosot_sot_pairs_scratch_bytes(n)), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         rc = lib.bosot_sot_pairs(
             trees.data_ptr(), n, C.byref(state.grammar.c_struct), state.blob.data_ptr(), E, _DBL3(*[float(w) for w in weights]),
             float(variance), float(lengthscale), _ptr(out.get("K")), _ptr(out.get("D")), _ptr(out.get("Df")), E,
-            status.data_ptr(), _stream(dev),
+            status.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream(dev),
         )
     _lib.check(rc, "sot_pairs")
     if check:

@@ -127,13 +127,16 @@ int bosot_eval_build(const uint8_t* d_trees, int n_eval, const bosot_grammar* gr
  *   D[c][e]     = sum_f weights[f] * Df[f][c][e]        (weights = alpha_f / sum(alpha), 0 = feature off)
  *   K[c][e]     = variance * exp(-D / lengthscale^2)
  * Outputs are [n_cand][ld] fp64 with leading dimension ld >= n_eval (Df: 3 planes of
- * n_cand*ld); any of d_K / d_D / d_Df may be NULL.  d_status: int32[n_cand] tree defects.
+ * n_cand*ld); any of d_K / d_D / d_Df may be NULL.  d_status: int32[n_cand] tree defects (may be NULL).
+ * d_scratch: device scratch of bosot_sot_pairs_scratch_bytes(n_cand) bytes, 16-byte aligned
+ * (compact per-tree records between the scan launch and the pair launch).
  */
+size_t bosot_sot_pairs_scratch_bytes(int64_t n_cand);
 int bosot_sot_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,
                     const void* d_eval_blob, int n_eval, const double weights[3],
                     double variance, double lengthscale,
                     double* d_K, double* d_D, double* d_Df, int64_t ld,
-                    int32_t* d_status, void* stream);
+                    int32_t* d_status, void* d_scratch, size_t scratch_bytes, void* stream);
 
 /* ---- GP posterior + acquisition -----------------------------------------------------
  * Inputs: K*[n_cand][ld] (rows = candidates), Linv[ldl][ldl] = inverse of the lower Cholesky
