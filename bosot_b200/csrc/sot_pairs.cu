@@ -103,6 +103,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // exp(x) for x <= 0 (the Gram argument -d / l^2): Cody-Waite reduction by ln 2, degree-13 Taylor
 // polynomial on |r| <= ln2 / 2 (truncation 4e-18 relative), scaling through the exponent field.
 // About half the instructions of the general exp(); the denormal / underflow tail takes the slow path.
+__device__ __noinline__ double exp_slow_path(double x) { return exp(x); }  // out of line: keeps the hot loop small
+
 __device__ __forceinline__ double exp_nonpos(double x) {
   const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
   const int n = __double2loint(t);
@@ -123,7 +125,7 @@ __device__ __forceinline__ double exp_nonpos(double x) {
   q = fma(q, r, 0.5);
   q = fma(q, r, 1.0);
   q = fma(q, r, 1.0);
-  if (n < -1021 || !(x <= 0.0)) return exp(x);  // underflow tail, NaN
+  if (n < -1021 || !(x <= 0.0)) return exp_slow_path(x);  // underflow tail, NaN
   return __hiloint2double(__double2hiint(q) + n * 1048576, __double2loint(q));
 }
 
@@ -226,8 +228,9 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     const bool bad = (cur.meta >> 24) != 0;
     const size_t row = (size_t)t * p.ld;
 
-    if (bad) {  // malformed record: poison the row, status already written by the scan
+    if (bad) {  // malformed record: poison the row, status already written by the scan (cold path: keep it small)
       const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll 1
       for (int e = lane; e < E; e += 32) {
         if (p.K) p.K[row + e] = qnan;
         if (p.D) p.D[row + e] = qnan;
@@ -237,8 +240,11 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     }
 
     __syncwarp();
+#pragma unroll 1
     for (int e = lane; e < e_pad; e += 32) acc[e] = 0u;
+#pragma unroll 1
     for (int s = lane; s < BOSOT_MAX_SYMBOLS + BOSOT_MAX_BLOCKS; s += 32) scnt[s] = 0u;
+#pragma unroll 1
     for (int c = lane; c < F; c += 32) avec[c] = 0.0;
     __syncwarp();
 
@@ -276,6 +282,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     __syncwarp();
 
     // candidate DIM_WISE vector from the symbol counts (optimal_transport_mappings.py:88-108)
+#pragma unroll 1
     for (int s = lane; s < g.n_symbols; s += 32) {
       const int b = g.sym_block[s], c = g.sym_col[s];
       if (b >= 0 && c >= 0) {
@@ -295,6 +302,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
         const uint32_t beg = __shfl_sync(full, r.x, src);
         const uint32_t len = __shfl_sync(full, r.y, src);
         const uint32_t ca = __shfl_sync(full, cnt_a, src);
+#pragma unroll 1
         for (uint32_t q = lane; q < len; q += 32) {
           const uint32_t pq = __ldg(&post[beg + q]);
           const uint32_t e = pq & 0xffffu, cb = (pq >> 16) & 0xffu, Tb = pq >> 24;
@@ -334,6 +342,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
       // DIM_WISE: dense L1 over the d * (kinds + 1) columns, column-outer so the candidate value is read once
       {
         const double* col = dimT + eb;
+#pragma unroll 2
         for (int c = 0; c < F; ++c, col += e_pad) {
           const double a = avec[c];
 #pragma unroll
