@@ -177,6 +177,215 @@ posterior_kernel(PostParams p) {
   }
 }
 
+// ---- warp-specialised variant -----------------------------------------------------------------
+// One persistent CTA per SM: warp 0 streams K* tiles (TC candidates) into a 2-stage shared-memory ring
+// with TMA bulk row copies completing on "full" mbarriers; the consumer warps pull (tile, unit) work
+// items from ONE shared queue -- units of a tile = its 16-row blocks of L^-1, largest first, then the
+// mean dot products -- so nobody ever waits at a CTA-wide barrier: the warp that completes the last
+// unit of a tile runs that tile's epilogue and hands the stage back through the "empty" mbarrier.
+constexpr int kWsConsumers = 8;
+constexpr int kWsThreads = (kWsConsumers + 1) * 32;
+
+__device__ __forceinline__ uint32_t ws_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ws_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ws_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ws_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ws_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ws_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ws_tma_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(ws_smem_u32(dst)), "l"(src), "r"(bytes), "r"(ws_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ws_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WS_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra WS_WAIT_%=;\n"
+      "}\n" ::"r"(ws_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+struct WsLayout {
+  size_t off_ks, off_red, off_mus, total;
+  int tld, n_blk;
+};
+template <int TC>
+__host__ __device__ inline WsLayout ws_layout(int E) {
+  WsLayout W;
+  W.tld = post_tile_ld(E);
+  W.n_blk = (E + kRowBlk - 1) / kRowBlk;
+  size_t o = 64;  // full[2], empty[2], next_work, done[2]
+  W.off_ks = o;   o += sizeof(double) * 2 * (size_t)TC * W.tld;
+  W.off_red = o;  o += sizeof(double) * 2 * (size_t)W.n_blk * TC;
+  W.off_mus = o;  o += sizeof(double) * 2 * TC;
+  W.total = o;
+  return W;
+}
+
+template <int TC>
+__global__ void __launch_bounds__(kWsThreads, 1)
+posterior_ws_kernel(PostParams p) {
+  constexpr int NB = TC / 8;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int E = p.E;
+  const WsLayout W = ws_layout<TC>(E);
+  const int tld = W.tld, n_blk = W.n_blk, n_units = n_blk + 1;
+  const int ks_max = (E + 3) >> 2;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + 2;
+  int* next_work = reinterpret_cast<int*>(smem + 32);
+  int* done = next_work + 1;  // [2]
+  double* Ks = reinterpret_cast<double*>(smem + W.off_ks);
+  double* red = reinterpret_cast<double*>(smem + W.off_red);
+  double* mus = reinterpret_cast<double*>(smem + W.off_mus);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+
+  const int64_t n_tiles = (p.n_cand + TC - 1) / TC;
+  const int n_my = blockIdx.x < n_tiles ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+
+  if (threadIdx.x == 0) {
+    ws_mbar_init(&full[0], 1); ws_mbar_init(&full[1], 1);
+    ws_mbar_init(&empty[0], 1); ws_mbar_init(&empty[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    *next_work = 0; done[0] = 0; done[1] = 0;
+  }
+  for (int x = threadIdx.x; x < 2 * TC * tld; x += kWsThreads) Ks[x] = 0.0;  // padding columns / unused rows stay finite
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");             // generic-proxy zeros before async-proxy writes
+  __syncthreads();
+
+  if (warp == kWsConsumers) {
+    // ---------------- producer: one lane issues the row copies of every tile of this CTA
+    if (lane == 0) {
+      for (int i = 0; i < n_my; ++i) {
+        const int s = i & 1;
+        if (i >= 2) ws_mbar_wait(&empty[s], ((i >> 1) - 1) & 1);
+        const int64_t c0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * TC;
+        const int rows = (int)min((int64_t)TC, p.n_cand - c0);
+        ws_mbar_expect_tx(&full[s], (uint32_t)rows * (uint32_t)E * 8u);
+        double* dst = Ks + (size_t)s * TC * tld;
+        for (int c = 0; c < rows; ++c) ws_tma_g2s(dst + (size_t)c * tld, p.Kstar + (c0 + c) * p.ld, (uint32_t)E * 8u, &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumers
+  while (true) {
+    int w = 0;
+    if (lane == 0) w = atomicAdd(next_work, 1);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    const int i = w / n_units, u = w - i * n_units;
+    if (i >= n_my) break;
+    const int s = i & 1;
+    ws_mbar_wait(&full[s], (i >> 1) & 1);
+    const double* Kt = Ks + (size_t)s * TC * tld;
+    double* red_s = red + (size_t)s * n_blk * TC;
+    double* mus_s = mus + (size_t)s * TC;
+
+    if (u < n_blk) {
+      const int m = n_blk - 1 - u;  // largest block first
+      const int i0 = m * kRowBlk;
+      const int nks = min(i0 / 4 + 4, ks_max);
+      const int nks_up = min(i0 / 4 + 2, ks_max);
+      const bool lower_live = i0 + 8 < E;
+      double up[NB][2], lo[NB][2];
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) { up[nb][0] = up[nb][1] = 0.0; lo[nb][0] = lo[nb][1] = 0.0; }
+      const double* a_up = p.Linv + (size_t)(i0 + g) * p.ldl + t;
+      const double* a_lo = a_up + (size_t)8 * p.ldl;
+      const double* bp = Kt + g * tld + t;
+      double an_up = __ldg(a_up), an_lo = lower_live ? __ldg(a_lo) : 0.0;
+      for (int ks = 0; ks < nks; ++ks) {
+        const double au = an_up, al = an_lo;
+        if (ks + 1 < nks) {
+          an_up = (ks + 1 < nks_up) ? __ldg(a_up + 4 * (ks + 1)) : 0.0;
+          an_lo = lower_live ? __ldg(a_lo + 4 * (ks + 1)) : 0.0;
+        }
+        double b[NB];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) b[nb] = bp[(size_t)nb * 8 * tld + 4 * ks];
+        if (ks < nks_up) {
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) dmma8x8x4(up[nb][0], up[nb][1], au, b[nb]);
+        }
+        if (lower_live) {
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) dmma8x8x4(lo[nb][0], lo[nb][1], al, b[nb]);
+        }
+      }
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        double s0 = fma(up[nb][0], up[nb][0], lo[nb][0] * lo[nb][0]);
+        double s1 = fma(up[nb][1], up[nb][1], lo[nb][1] * lo[nb][1]);
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        if (g == 0) {
+          red_s[m * TC + nb * 8 + 2 * t] = s0;
+          red_s[m * TC + nb * 8 + 2 * t + 1] = s1;
+        }
+      }
+    } else {
+      // mean unit: K* . beta for the TC candidates of the tile (same 4-way split per candidate as the generic kernel)
+      for (int c = lane >> 2; c < TC; c += 8) {
+        const int q = lane & 3;
+        double sacc = 0.0;
+        for (int j = q; j < E; j += 4) sacc = fma(Kt[c * tld + j], __ldg(&p.beta[j]), sacc);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+        if (q == 0) mus_s[c] = sacc + p.mean_c;
+      }
+    }
+
+    // publish this unit; the warp that completes the tile runs its epilogue and frees the stage
+    __threadfence_block();
+    int d = 0;
+    if (lane == 0) d = atomicAdd(&done[s], 1);
+    d = __shfl_sync(0xffffffffu, d, 0);
+    if (d == n_units - 1) {
+      __threadfence_block();
+      const int64_t c0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * TC;
+      const int in_tile = (int)min((int64_t)TC, p.n_cand - c0);
+      for (int c = lane; c < in_tile; c += 32) {
+        double ss = 0.0;
+        for (int m = 0; m < n_blk; ++m) ss += red_s[m * TC + c];
+        const double var = p.variance - ss;
+        const double sg = sqrt(var);
+        const double mval = mus_s[c];
+        if (p.mu) p.mu[c0 + c] = mval;
+        if (p.sigma) p.sigma[c0 + c] = sg;
+        if (p.acq) {
+          double a;
+          if (p.acq_kind == BOSOT_ACQ_EI) {
+            const double dd = mval - *p.cur_max - p.xi;
+            const double z = dd / sg;
+            a = dd * norm_cdf(z) + sg * norm_pdf(z);
+          } else if (p.acq_kind == BOSOT_ACQ_UCB) {
+            a = mval + p.sqrt_ucb_beta * sg;
+          } else {
+            a = mval;
+          }
+          p.acq[c0 + c] = a;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        done[s] = 0;
+        __threadfence_block();
+        ws_mbar_arrive(&empty[s]);
+      }
+    }
+  }
+}
+
 __global__ void max_f64_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ out) {
   __shared__ double part[32];
   double m = -INFINITY;
@@ -237,15 +446,41 @@ int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_ev
   p.acq_kind = acq_kind; p.cur_max = d_current_max; p.xi = xi; p.sqrt_ucb_beta = sqrt(ucb_beta);
   p.mu = d_mu; p.sigma = d_sigma; p.acq = d_acq;
 
-  const int n_blk = (n_eval + kRowBlk - 1) / kRowBlk;
-  const size_t smem = sizeof(double) * ((size_t)kPostCand * post_tile_ld(n_eval) + (size_t)n_blk * kPostCand + kPostCand) + 16;
-  if (smem > 226 * 1024) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: n_eval too large for shared memory");
-  static bool attr_set[64] = {false};
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   if (int rc = cuda_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return rc;
+  const size_t smem_cap = 226 * 1024;
+
+  // warp-specialised TMA variant: needs 16-byte aligned rows of whole 16-byte units
+  const bool tma_ok = (n_eval % 2 == 0) && (ld % 2 == 0) && !(reinterpret_cast<uintptr_t>(d_Kstar) & 15);
+  if (tma_ok) {
+    static bool ws_attr[64] = {false};
+    if (!(dev < 64 && ws_attr[dev])) {
+      if (int rc = cuda_check(cudaFuncSetAttribute(posterior_ws_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
+                              "cudaFuncSetAttribute(posterior_ws_kernel<64>)")) return rc;
+      if (int rc = cuda_check(cudaFuncSetAttribute(posterior_ws_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
+                              "cudaFuncSetAttribute(posterior_ws_kernel<32>)")) return rc;
+      if (dev < 64) ws_attr[dev] = true;
+    }
+    const size_t s64 = ws_layout<64>(n_eval).total, s32 = ws_layout<32>(n_eval).total;
+    if (s64 <= smem_cap) {
+      const int64_t tiles = (n_cand + 63) / 64;
+      posterior_ws_kernel<64><<<(unsigned)(tiles < sms ? tiles : sms), kWsThreads, s64, stream>>>(p);
+      return after_launch("posterior_ws_kernel<64>");
+    }
+    if (s32 <= smem_cap) {
+      const int64_t tiles = (n_cand + 31) / 32;
+      posterior_ws_kernel<32><<<(unsigned)(tiles < sms ? tiles : sms), kWsThreads, s32, stream>>>(p);
+      return after_launch("posterior_ws_kernel<32>");
+    }
+  }
+
+  const int n_blk = (n_eval + kRowBlk - 1) / kRowBlk;
+  const size_t smem = sizeof(double) * ((size_t)kPostCand * post_tile_ld(n_eval) + (size_t)n_blk * kPostCand + kPostCand) + 16;
+  if (smem > smem_cap) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: n_eval too large for shared memory");
+  static bool attr_set[64] = {false};
   if (!(dev < 64 && attr_set[dev])) {
-    if (int rc = cuda_check(cudaFuncSetAttribute(posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024),
+    if (int rc = cuda_check(cudaFuncSetAttribute(posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
                             "cudaFuncSetAttribute(posterior_kernel)")) return rc;
     if (dev < 64) attr_set[dev] = true;
   }

@@ -101,32 +101,44 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // exp(x) for x <= 0 (the Gram argument -d / l^2): Cody-Waite reduction by ln 2, degree-13 Taylor
-// polynomial on |r| <= ln2 / 2 (truncation 4e-18 relative), scaling through the exponent field.
-// About half the instructions of the general exp(); the denormal / underflow tail takes the slow path.
-__device__ __noinline__ double exp_slow_path(double x) { return exp(x); }  // out of line: keeps the hot loop small
+// polynomial on |r| <= ln2 / 2 (truncation 4e-18 relative), scaling by 2^n in two exact steps so
+// that results in the denormal range underflow gradually without a slow path.  The coefficients
+// live in constant memory: as immediates every one of them costs two extra UMOV per use.
+__constant__ double c_exp[16] = {
+    1.4426950408889634074,       // [0] log2(e)
+    6755399441055744.0,          // [1] 1.5 * 2^52: rounds to nearest integer in the low mantissa bits
+    -6.93147180369123816490e-01, // [2] -ln2 (high part, 32 trailing zero bits)
+    -1.90821492927058770002e-10, // [3] -ln2 (low part)
+    1.6059043836821613e-10,      // [4] 1/13!
+    2.08767569878681e-09,        // [5] 1/12!
+    2.505210838544172e-08,       // [6] 1/11!
+    2.755731922398589e-07,       // [7] 1/10!
+    2.7557319223985893e-06,      // [8] 1/9!
+    2.48015873015873e-05,        // [9] 1/8!
+    1.984126984126984e-04,       // [10] 1/7!
+    1.388888888888889e-03,       // [11] 1/6!
+    8.333333333333333e-03,       // [12] 1/5!
+    4.1666666666666664e-02,      // [13] 1/4!
+    1.6666666666666666e-01,      // [14] 1/3!
+    -1400.0};                    // [15] clamp: exp(-1400) == 0 in fp64, keeps both scale factors normal
 
 __device__ __forceinline__ double exp_nonpos(double x) {
-  const double t = fma(x, 1.4426950408889634074, 6755399441055744.0);
+  x = x < c_exp[15] ? c_exp[15] : x;  // NaN stays NaN
+  const double t = fma(x, c_exp[0], c_exp[1]);
   const int n = __double2loint(t);
-  const double nf = t - 6755399441055744.0;
-  double r = fma(nf, -6.93147180369123816490e-01, x);
-  r = fma(nf, -1.90821492927058770002e-10, r);
-  double q = 1.6059043836821613e-10;           // 1/13!
-  q = fma(q, r, 2.08767569878681e-09);         // 1/12!
-  q = fma(q, r, 2.505210838544172e-08);        // 1/11!
-  q = fma(q, r, 2.755731922398589e-07);        // 1/10!
-  q = fma(q, r, 2.7557319223985893e-06);       // 1/9!
-  q = fma(q, r, 2.48015873015873e-05);         // 1/8!
-  q = fma(q, r, 1.984126984126984e-04);        // 1/7!
-  q = fma(q, r, 1.388888888888889e-03);        // 1/6!
-  q = fma(q, r, 8.333333333333333e-03);        // 1/5!
-  q = fma(q, r, 4.1666666666666664e-02);       // 1/4!
-  q = fma(q, r, 1.6666666666666666e-01);       // 1/3!
+  const double nf = t - c_exp[1];
+  double r = fma(nf, c_exp[2], x);
+  r = fma(nf, c_exp[3], r);
+  double q = c_exp[4];
+#pragma unroll
+  for (int k = 5; k <= 14; ++k) q = fma(q, r, c_exp[k]);
   q = fma(q, r, 0.5);
   q = fma(q, r, 1.0);
   q = fma(q, r, 1.0);
-  if (n < -1021 || !(x <= 0.0)) return exp_slow_path(x);  // underflow tail, NaN
-  return __hiloint2double(__double2hiint(q) + n * 1048576, __double2loint(q));
+  const int n1 = n >> 1, n2 = n - n1;  // 2^n = 2^n1 * 2^n2, both factors normal for n >= -2044
+  const double s1 = __hiloint2double((1023 + n1) << 20, 0);
+  const double s2 = __hiloint2double((1023 + n2) << 20, 0);
+  return (q * s1) * s2;
 }
 
 // ---- launch 1: thread-per-tree scan -> compact records ------------------------------------
@@ -292,23 +304,37 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     }
     if (lane < g.n_blocks) avec[g.block_null_col[lane]] = btot[lane] == 0u ? 1.0 : 0.0;
 
-    // walk the postings of every matched feature; all postings of one feature belong to
-    // distinct evaluated trees, so the read-modify-write of acc[e] needs no atomics
+    // Walk the postings of all matched features as ONE flattened list: an exclusive scan of the list
+    // lengths over the lanes gives every feature its segment; in each round lane j takes posting
+    // q = 32 * round + j and finds its feature by a 5-step binary search over the segment starts
+    // (register shuffles).  Full rounds instead of one mostly empty round per feature; postings of
+    // different features may hit the same evaluated tree, hence the shared-memory atomic.
     auto walk = [&](uint2 r, uint32_t cnt_a, uint32_t Ta, int shift) {
-      unsigned todo = __ballot_sync(full, r.y != 0u);
-      while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint32_t beg = __shfl_sync(full, r.x, src);
-        const uint32_t len = __shfl_sync(full, r.y, src);
-        const uint32_t ca = __shfl_sync(full, cnt_a, src);
+      uint32_t inc = r.y;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(full, inc, o);
+        if (lane >= o) inc += v;
+      }
+      const uint32_t total = __shfl_sync(full, inc, 31);
+      const uint32_t start = inc - r.y;
 #pragma unroll 1
-        for (uint32_t q = lane; q < len; q += 32) {
-          const uint32_t pq = __ldg(&post[beg + q]);
-          const uint32_t e = pq & 0xffffu, cb = (pq >> 16) & 0xffu, Tb = pq >> 24;
-          acc[e] += min(ca * Tb, cb * Ta) << shift;
+      for (uint32_t q0 = 0; q0 < total; q0 += 32) {
+        const uint32_t q = q0 + lane;
+        int k = 0;  // largest lane whose segment starts at or before q
+#pragma unroll
+        for (int step = 16; step; step >>= 1) {
+          const uint32_t sk = __shfl_sync(full, start, k + step);
+          if (sk <= q) k += step;
         }
-        __syncwarp();
+        const uint32_t beg = __shfl_sync(full, r.x, k);
+        const uint32_t st = __shfl_sync(full, start, k);
+        const uint32_t ca = __shfl_sync(full, cnt_a, k);
+        if (q < total) {
+          const uint32_t pq = __ldg(&post[beg + (q - st)]);
+          const uint32_t e = pq & 0xffffu, cb = (pq >> 16) & 0xffu, Tb = pq >> 24;
+          atomicAdd(&acc[e], min(ca * Tb, cb * Ta) << shift);
+        }
       }
     };
     walk(r_int, (uint32_t)__popc(m_id), (uint32_t)nn, 0);
