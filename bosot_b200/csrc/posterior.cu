@@ -34,8 +34,8 @@ struct PostParams {
   int64_t n_cand;
   int64_t ld;
   int E;
-  int ldl;  // leading dimension (and padded row count) of Linv: multiple of 16, zero padded
-  const double* Linv;
+  int ldl;  // padded order of L^-1: multiple of 16
+  const double* Linv;  // FRAGMENT-MAJOR: LinvF[(rb * ldl/4 + ks) * 32 + 4 g + t] = Linv[8 rb + g][4 ks + t] (bosot_pack_linv)
   const double* beta;
   double mean_c, variance;
   int acq_kind;
@@ -111,15 +111,16 @@ posterior_kernel(PostParams p) {
       double up[kNB][2], lo[kNB][2];
 #pragma unroll
       for (int nb = 0; nb < kNB; ++nb) { up[nb][0] = up[nb][1] = 0.0; lo[nb][0] = lo[nb][1] = 0.0; }
-      const double* a_up = p.Linv + (size_t)(i0 + g) * p.ldl + t;
-      const double* a_lo = a_up + (size_t)8 * p.ldl;
+      const int KS = p.ldl >> 2;
+      const double* a_up = p.Linv + (size_t)(2 * m) * KS * 32 + lane;  // one coalesced 256-byte fragment per k-step
+      const double* a_lo = a_up + (size_t)KS * 32;
       const double* bp = Ks + g * tld + t;
       double an_up = __ldg(a_up), an_lo = lower_live ? __ldg(a_lo) : 0.0;
       for (int ks = 0; ks < nks; ++ks) {
         const double au = an_up, al = an_lo;
         if (ks + 1 < nks) {  // prefetch the next A fragments (L2 latency) behind this step's 16 DMMAs
-          an_up = (ks + 1 < nks_up) ? __ldg(a_up + 4 * (ks + 1)) : 0.0;
-          an_lo = lower_live ? __ldg(a_lo + 4 * (ks + 1)) : 0.0;
+          an_up = (ks + 1 < nks_up) ? __ldg(a_up + 32 * (ks + 1)) : 0.0;
+          an_lo = lower_live ? __ldg(a_lo + 32 * (ks + 1)) : 0.0;
         }
         double b[kNB];
 #pragma unroll
@@ -255,7 +256,7 @@ posterior_ws_kernel(PostParams p) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     *next_work = 0; done[0] = 0; done[1] = 0;
   }
-  for (int x = threadIdx.x; x < 2 * TC * tld; x += kWsThreads) Ks[x] = 0.0;  // padding columns / unused rows stay finite
+  for (int x = threadIdx.x; x < (int)((W.total - W.off_ks) / sizeof(double)); x += kWsThreads) Ks[x] = 0.0;  // everything finite
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");             // generic-proxy zeros before async-proxy writes
   __syncthreads();
 
@@ -297,26 +298,46 @@ posterior_ws_kernel(PostParams p) {
       double up[NB][2], lo[NB][2];
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) { up[nb][0] = up[nb][1] = 0.0; lo[nb][0] = lo[nb][1] = 0.0; }
-      const double* a_up = p.Linv + (size_t)(i0 + g) * p.ldl + t;
-      const double* a_lo = a_up + (size_t)8 * p.ldl;
+      // Software pipeline: A fragments (L^-1, from L2) run kPD k-steps ahead in a register ring, B fragments
+      // (K* tile, shared memory) one k-step ahead, so the 16 DMMAs of a step never wait on a load of that step.
+      // The k range is padded to a multiple of kPD: the extra steps multiply structural zeros of L^-1.
+      constexpr int kPD = 4;
+      const int KS = p.ldl >> 2;
+      const double* a_up = p.Linv + (size_t)(2 * m) * KS * 32 + lane;  // one coalesced 256-byte fragment per k-step
+      const double* a_lo = a_up + (size_t)KS * 32;
       const double* bp = Kt + g * tld + t;
-      double an_up = __ldg(a_up), an_lo = lower_live ? __ldg(a_lo) : 0.0;
-      for (int ks = 0; ks < nks; ++ks) {
-        const double au = an_up, al = an_lo;
-        if (ks + 1 < nks) {
-          an_up = (ks + 1 < nks_up) ? __ldg(a_up + 4 * (ks + 1)) : 0.0;
-          an_lo = lower_live ? __ldg(a_lo + 4 * (ks + 1)) : 0.0;
-        }
-        double b[NB];
+      const int nks_pad = (nks + kPD - 1) & ~(kPD - 1);
+      double ra_up[kPD], ra_lo[kPD], b_cur[NB], b_nxt[NB];
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) b[nb] = bp[(size_t)nb * 8 * tld + 4 * ks];
-        if (ks < nks_up) {
+      for (int u = 0; u < kPD; ++u) {
+        ra_up[u] = __ldg(a_up + 32 * u);
+        ra_lo[u] = lower_live ? __ldg(a_lo + 32 * u) : 0.0;
+      }
 #pragma unroll
-          for (int nb = 0; nb < NB; ++nb) dmma8x8x4(up[nb][0], up[nb][1], au, b[nb]);
-        }
-        if (lower_live) {
+      for (int nb = 0; nb < NB; ++nb) b_cur[nb] = bp[(size_t)nb * 8 * tld];
+      for (int ks0 = 0; ks0 < nks_pad; ks0 += kPD) {
 #pragma unroll
-          for (int nb = 0; nb < NB; ++nb) dmma8x8x4(lo[nb][0], lo[nb][1], al, b[nb]);
+        for (int u = 0; u < kPD; ++u) {
+          const int ks = ks0 + u;
+          const double au = ra_up[u], al = ra_lo[u];
+          if (ks + kPD < nks_pad) {
+            ra_up[u] = __ldg(a_up + 32 * (ks + kPD));
+            ra_lo[u] = lower_live ? __ldg(a_lo + 32 * (ks + kPD)) : 0.0;
+          }
+          if (ks + 1 < nks_pad) {
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) b_nxt[nb] = bp[(size_t)nb * 8 * tld + 4 * (ks + 1)];
+          }
+          if (ks < nks_up) {
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) dmma8x8x4(up[nb][0], up[nb][1], au, b_cur[nb]);
+          }
+          if (lower_live) {
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) dmma8x8x4(lo[nb][0], lo[nb][1], al, b_cur[nb]);
+          }
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) b_cur[nb] = b_nxt[nb];
         }
       }
 #pragma unroll
@@ -384,6 +405,17 @@ posterior_ws_kernel(PostParams p) {
       }
     }
   }
+}
+
+// row-major L^-1 (n x n, leading dimension ld_src) -> zero-padded fragment-major copy of order ldl
+__global__ void pack_linv_kernel(const double* __restrict__ src, int n, int ld_src, double* __restrict__ dst, int ldl) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= ldl * ldl) return;
+  const int KS = ldl >> 2;
+  const int l = x & 31, f = x >> 5;       // lane within fragment, fragment index = rb * KS + ks
+  const int rb = f / KS, ks = f - rb * KS;
+  const int i = 8 * rb + (l >> 2), j = 4 * ks + (l & 3);
+  dst[x] = (i < n && j < n && j <= i) ? src[(size_t)i * ld_src + j] : 0.0;
 }
 
 __global__ void max_f64_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ out) {
@@ -498,6 +530,12 @@ int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_ev
 }  // namespace bosot
 
 using namespace bosot;
+
+extern "C" int bosot_pack_linv(const double* d_Linv, int n, int ld_src, double* d_LinvF, int ldl, void* stream) {
+  if (!d_Linv || !d_LinvF || n < 1 || ld_src < n || ldl < n || (ldl % 16) != 0) return set_error(BOSOT_EINVAL, "bosot_pack_linv: bad argument");
+  pack_linv_kernel<<<(ldl * ldl + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_Linv, n, ld_src, d_LinvF, ldl);
+  return after_launch("pack_linv_kernel");
+}
 
 extern "C" int bosot_max_f64(const double* d_x, int64_t n, double* d_out, void* stream) {
   if (!d_x || !d_out || n < 1) return set_error(BOSOT_EINVAL, "bosot_max_f64: bad argument");

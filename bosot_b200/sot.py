@@ -185,7 +185,8 @@ def sot_pairs(
 def gp_factorize(K_EE: torch.Tensor, noise_variance: float, err: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """Small E x E part of the posterior, left to cuSOLVER/cuBLAS via torch.linalg:
     Lm = chol(K_EE + s^2 I) (GPflow ``base_conditional``), returns
-    (Linv = Lm^-1 zero-padded to [ldl, ldl] with ldl a multiple of 16, beta = (K_EE + s^2 I)^-1 err).
+    (LinvF = Lm^-1 packed by ``bosot_pack_linv`` into the zero-padded fragment-major layout of order
+    ldl (multiple of 16) that the posterior kernel's fp64 tensor-core tiles read, beta = (K_EE + s^2 I)^-1 err).
     Raises like the reference's TF Cholesky when the matrix is not positive definite."""
     E = K_EE.shape[0]
     A = K_EE + noise_variance * torch.eye(E, dtype=torch.float64, device=K_EE.device)
@@ -194,8 +195,10 @@ def gp_factorize(K_EE: torch.Tensor, noise_variance: float, err: torch.Tensor) -
         raise RuntimeError("Cholesky decomposition was not successful (leading minor %d not positive definite)" % int(info))
     eye = torch.eye(E, dtype=torch.float64, device=K_EE.device)
     ldl = (E + 15) // 16 * 16
-    Linv = torch.zeros((ldl, ldl), dtype=torch.float64, device=K_EE.device)
-    Linv[:E, :E] = torch.tril(torch.linalg.solve_triangular(L, eye, upper=False))
+    Linv_rm = torch.linalg.solve_triangular(L, eye, upper=False).contiguous()
+    Linv = torch.empty((ldl, ldl), dtype=torch.float64, device=K_EE.device)
+    with torch.cuda.device(K_EE.device):
+        _lib.check(_lib.load().bosot_pack_linv(Linv_rm.data_ptr(), E, E, Linv.data_ptr(), ldl, _stream(K_EE.device)), "pack_linv")
     beta = torch.cholesky_solve(err.reshape(E, 1), L).reshape(E).contiguous()
     return Linv, beta
 

@@ -139,9 +139,11 @@ int bosot_sot_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar*
                     int32_t* d_status, void* d_scratch, size_t scratch_bytes, void* stream);
 
 /* ---- GP posterior + acquisition -----------------------------------------------------
- * Inputs: K*[n_cand][ld] (rows = candidates), Linv[ldl][ldl] = inverse of the lower Cholesky
- * factor of K_EE + noise*I (row-major, lower triangular, ldl >= n_eval a multiple of 16, rows and
- * columns >= n_eval zero), beta[n_eval] = (K_EE + noise*I)^-1 (y - c).
+ * Inputs: K*[n_cand][ld] (rows = candidates), LinvF = inverse of the lower Cholesky factor of
+ * K_EE + noise*I in the zero-padded fragment-major layout written by bosot_pack_linv (order ldl >= n_eval,
+ * a multiple of 16): LinvF[(rb * ldl/4 + ks) * 32 + 4 g + t] = Linv[8 rb + g][4 ks + t], i.e. one coalesced
+ * 256-byte A fragment of the fp64 tensor-core tile per (row block, k-step);
+ * beta[n_eval] = (K_EE + noise*I)^-1 (y - c).
  *   mu    = K* . beta + mean_c
  *   var   = variance - || L^-1 k* ||^2          (K_diag == variance: d(x,x) = 0 exactly)
  *   sigma = sqrt(var)                           (NaN if var < 0, as in the reference)
@@ -153,8 +155,10 @@ int bosot_sot_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar*
 #define BOSOT_ACQ_EI 1
 #define BOSOT_ACQ_UCB 2
 
+int bosot_pack_linv(const double* d_Linv /* row-major [n][ld_src], lower triangular */, int n, int ld_src,
+                    double* d_LinvF /* [ldl*ldl] */, int ldl, void* stream);
 int bosot_posterior_acq(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval,
-                        const double* d_Linv, int ldl, const double* d_beta, double mean_c, double variance,
+                        const double* d_LinvF, int ldl, const double* d_beta, double mean_c, double variance,
                         int acq_kind, const double* d_current_max, double xi, double ucb_beta,
                         double* d_mu, double* d_sigma, double* d_acq, void* stream);
 
@@ -171,7 +175,7 @@ size_t bosot_acquire_work_bytes(int64_t n_cand, int n_eval);
 int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const bosot_grammar* grammar,
                        const void* d_eval_blob, int n_eval, const double weights[3],
                        double variance, double lengthscale,
-                       const double* d_Linv, int ldl, const double* d_beta, double mean_c,
+                       const double* d_LinvF, int ldl, const double* d_beta, double mean_c,
                        int acq_kind, const double* d_current_max, double xi, double ucb_beta,
                        void* d_work, size_t work_bytes,
                        double* h_mu, double* h_sigma, double* h_acq, void* stream);
@@ -180,7 +184,7 @@ int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const bosot_gramm
 int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,
                          const void* d_eval_blob, int n_eval, const double weights[3],
                          double variance, double lengthscale,
-                         const double* d_Linv, int ldl, const double* d_beta, double mean_c,
+                         const double* d_LinvF, int ldl, const double* d_beta, double mean_c,
                          int acq_kind, const double* d_current_max, double xi, double ucb_beta,
                          void* d_work, size_t work_bytes,
                          double* d_mu, double* d_sigma, double* d_acq, void* stream);
