@@ -71,6 +71,7 @@ SIGNATURES = {
     ),
     "bosot_fp64_fma_probe": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "bosot_fp64_mma_probe": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
+    "bosot_fp64_mma_probe2": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "bosot_kernel_launch_count": (C.c_int64, []),
 }
 

@@ -462,6 +462,42 @@ __global__ void fp64_mma_probe_kernel(double* out, int iters) {
   if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// register-pattern probes: NA A-fragments x NB B-fragments -> NA*NB accumulator tiles per step (no loads).
+// A_OUTER: for a { for b { mma(acc[a][b], A[a], B[b]) } }  (A stationary), else B stationary.
+template <int NA, int NBF, bool A_OUTER>
+__global__ void fp64_mma_pattern_kernel(double* out, int iters) {
+  double acc[NA][NBF][2], a[NA], b[NBF];
+#pragma unroll
+  for (int i = 0; i < NA; ++i) { a[i] = 1.0 - 1e-9 * (threadIdx.x + i);
+#pragma unroll
+    for (int j = 0; j < NBF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0; }
+#pragma unroll
+  for (int j = 0; j < NBF; ++j) b[j] = 1.0 + 1e-9 * (threadIdx.x + j);
+  for (int it = 0; it < iters; ++it) {
+    if (A_OUTER) {
+#pragma unroll
+      for (int i = 0; i < NA; ++i)
+#pragma unroll
+        for (int j = 0; j < NBF; ++j) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NBF; ++j)
+#pragma unroll
+        for (int i = 0; i < NA; ++i) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < NA; ++i) a[i] += 1e-12;
+#pragma unroll
+    for (int j = 0; j < NBF; ++j) b[j] += 1e-13;
+  }
+  double sacc = 0.0;
+#pragma unroll
+  for (int i = 0; i < NA; ++i)
+#pragma unroll
+    for (int j = 0; j < NBF; ++j) sacc += acc[i][j][0] + acc[i][j][1];
+  if (sacc == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = sacc;
+}
+
 int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval, const double* d_Linv, int ldl,
                      const double* d_beta, double mean_c, double variance, int acq_kind, const double* d_current_max,
                      double xi, double ucb_beta, double* d_mu, double* d_sigma, double* d_acq, cudaStream_t stream) {
@@ -547,6 +583,28 @@ extern "C" int bosot_fp64_mma_probe(double* d_out, int n_blocks, int n_threads, 
   if (!d_out || n_blocks < 1 || n_threads < 32 || n_threads > 1024 || iters < 1) return set_error(BOSOT_EINVAL, "bosot_fp64_mma_probe: bad argument");
   fp64_mma_probe_kernel<<<n_blocks, n_threads, 0, (cudaStream_t)stream>>>(d_out, iters);
   return after_launch("fp64_mma_probe_kernel");
+}
+
+extern "C" int bosot_fp64_mma_probe2(double* d_out, int n_blocks, int n_threads, int iters, void* stream) {
+  if (!d_out || n_blocks < 1 || n_threads < 32 || n_threads > 1024 || iters < 1) return set_error(BOSOT_EINVAL, "bosot_fp64_mma_probe2: bad argument");
+  // `iters` low 4 bits select the pattern (measurement tool only)
+  const int pat = iters & 15;
+  const int it = iters >> 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (pat) {
+    case 0: fp64_mma_pattern_kernel<2, 8, true><<<n_blocks, n_threads, 0, st>>>(d_out, it); break;
+    case 1: fp64_mma_pattern_kernel<2, 8, false><<<n_blocks, n_threads, 0, st>>>(d_out, it); break;
+    case 2: fp64_mma_pattern_kernel<4, 4, true><<<n_blocks, n_threads, 0, st>>>(d_out, it); break;
+    case 3: fp64_mma_pattern_kernel<4, 4, false><<<n_blocks, n_threads, 0, st>>>(d_out, it); break;
+    case 4: fp64_mma_pattern_kernel<8, 2, true><<<n_blocks, n_threads, 0, st>>>(d_out, it); break;
+    case 5: fp64_mma_pattern_kernel<8, 2, false><<<n_blocks, n_threads, 0, st>>>(d_out, it); break;
+    case 6: fp64_mma_pattern_kernel<1, 8, true><<<n_blocks, n_threads, 0, st>>>(d_out, it); break;
+    case 7: fp64_mma_pattern_kernel<8, 1, false><<<n_blocks, n_threads, 0, st>>>(d_out, it); break;
+    case 8: fp64_mma_pattern_kernel<1, 16, true><<<n_blocks, n_threads, 0, st>>>(d_out, it); break;
+    case 9: fp64_mma_pattern_kernel<16, 1, false><<<n_blocks, n_threads, 0, st>>>(d_out, it); break;
+    default: return set_error(BOSOT_EINVAL, "bosot_fp64_mma_probe2: unknown pattern");
+  }
+  return after_launch("fp64_mma_pattern_kernel");
 }
 
 extern "C" int bosot_fp64_fma_probe(double* d_out, int n_blocks, int n_threads, int iters, void* stream) {

@@ -196,6 +196,7 @@ int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, const bosot_gra
  * bosot_kernel_launch_count: number of kernels this library has launched in this process. */
 int bosot_fp64_fma_probe(double* d_out, int n_blocks, int n_threads, int iters, void* stream);
 int bosot_fp64_mma_probe(double* d_out, int n_blocks, int n_threads, int iters, void* stream);
+int bosot_fp64_mma_probe2(double* d_out, int n_blocks, int n_threads, int iters, void* stream); /* 2 A x 8 B fragments, 16 accumulator tiles */
 int64_t bosot_kernel_launch_count(void);
 
 #ifdef __cplusplus
