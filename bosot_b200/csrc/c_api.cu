@@ -1,6 +1,7 @@
 // C-ABI glue: error state, launch bookkeeping, argument checks and the composed
 // "acquire" entry points (pairs -> posterior -> acquisition) with host or device buffers.
 #include <atomic>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include "sot_common.cuh"
@@ -111,6 +112,40 @@ extern "C" int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, cons
                           ucb_beta, d_mu, d_sigma, d_acq, st);
 }
 
+// helper streams / events for the pipelined host entry point (created lazily, one set per device, never destroyed)
+namespace bosot {
+constexpr int kMaxChunks = 16;
+struct HostPipe {
+  bool ready = false;
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t start = nullptr, done = nullptr, copied[kMaxChunks] = {}, computed[kMaxChunks] = {};
+};
+static HostPipe g_pipe[64];
+static std::mutex g_pipe_mutex;  // the helper events are per device: serialise the (short) enqueue section
+
+static int host_pipe(int dev, HostPipe** out) {
+  if (dev < 0 || dev >= 64) return set_error(BOSOT_EINVAL, "bosot_acquire_host: device index out of range");
+  HostPipe& P = g_pipe[dev];
+  if (!P.ready) {
+    if (int rc = cuda_check(cudaStreamCreateWithFlags(&P.h2d, cudaStreamNonBlocking), "cudaStreamCreate(h2d)")) return rc;
+    if (int rc = cuda_check(cudaStreamCreateWithFlags(&P.d2h, cudaStreamNonBlocking), "cudaStreamCreate(d2h)")) return rc;
+    if (int rc = cuda_check(cudaEventCreateWithFlags(&P.start, cudaEventDisableTiming), "cudaEventCreate")) return rc;
+    if (int rc = cuda_check(cudaEventCreateWithFlags(&P.done, cudaEventDisableTiming), "cudaEventCreate")) return rc;
+    for (int k = 0; k < kMaxChunks; ++k) {
+      if (int rc = cuda_check(cudaEventCreateWithFlags(&P.copied[k], cudaEventDisableTiming), "cudaEventCreate")) return rc;
+      if (int rc = cuda_check(cudaEventCreateWithFlags(&P.computed[k], cudaEventDisableTiming), "cudaEventCreate")) return rc;
+    }
+    P.ready = true;
+  }
+  *out = &P;
+  return BOSOT_OK;
+}
+}  // namespace bosot
+
+// Host buffers in, host buffers out.  Large pools are cut into chunks that flow through a three-stage
+// pipeline on three streams -- H2D of chunk k+1 (copy engine) | kernels of chunk k (caller's stream) |
+// D2H of chunk k-1 (second copy engine) -- joined back into the caller's stream with events, so the call
+// keeps its contract: asynchronous, ordered on `stream`, the caller synchronises `stream`.
 extern "C" int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const bosot_grammar* grammar,
                                   const void* d_eval_blob, int n_eval, const double weights[3],
                                   double variance, double lengthscale,
@@ -126,16 +161,50 @@ extern "C" int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const 
   uint8_t* w = static_cast<uint8_t*>(d_work);
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* d_trees = w + W.off_trees;
+  double* d_K = reinterpret_cast<double*>(w + W.off_K);
   double* d_mu = reinterpret_cast<double*>(w + W.off_mu);
   double* d_sigma = reinterpret_cast<double*>(w + W.off_sigma);
   double* d_acq = reinterpret_cast<double*>(w + W.off_acq);
-  if (int rc = cuda_check(cudaMemcpyAsync(d_trees, h_trees, (size_t)n_cand * kTreeBytes, cudaMemcpyHostToDevice, st), "H2D trees")) return rc;
-  if (int rc = bosot_acquire_device(d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale, d_Linv,
-                                    ldl, d_beta, mean_c, acq_kind, d_current_max, xi, ucb_beta, d_work, work_bytes,
-                                    h_mu ? d_mu : nullptr, h_sigma ? d_sigma : nullptr, h_acq ? d_acq : nullptr, stream)) return rc;
-  const size_t nb = sizeof(double) * (size_t)n_cand;
-  if (h_mu) if (int rc = cuda_check(cudaMemcpyAsync(h_mu, d_mu, nb, cudaMemcpyDeviceToHost, st), "D2H mu")) return rc;
-  if (h_sigma) if (int rc = cuda_check(cudaMemcpyAsync(h_sigma, d_sigma, nb, cudaMemcpyDeviceToHost, st), "D2H sigma")) return rc;
-  if (h_acq) if (int rc = cuda_check(cudaMemcpyAsync(h_acq, d_acq, nb, cudaMemcpyDeviceToHost, st), "D2H acq")) return rc;
-  return BOSOT_OK;
+  int32_t* d_status = reinterpret_cast<int32_t*>(w + W.off_status);
+  uint8_t* d_recs = w + W.off_recs;
+
+  int dev = 0;
+  if (int rc = cuda_check(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+  std::lock_guard<std::mutex> lock(g_pipe_mutex);
+  HostPipe* P = nullptr;
+  if (int rc = host_pipe(dev, &P)) return rc;
+
+  int n_chunks = (int)(n_cand / 200000);
+  if (n_chunks < 1) n_chunks = 1;
+  if (n_chunks > kMaxChunks) n_chunks = kMaxChunks;
+  const int64_t per = ((n_cand + n_chunks - 1) / n_chunks + 63) & ~(int64_t)63;  // whole posterior tiles per chunk
+
+  // fork: both copy streams start after everything already queued on the caller's stream
+  if (int rc = cuda_check(cudaEventRecord(P->start, st), "cudaEventRecord")) return rc;
+  if (int rc = cuda_check(cudaStreamWaitEvent(P->h2d, P->start, 0), "cudaStreamWaitEvent")) return rc;
+  if (int rc = cuda_check(cudaStreamWaitEvent(P->d2h, P->start, 0), "cudaStreamWaitEvent")) return rc;
+  for (int k = 0; k < n_chunks; ++k) {
+    const int64_t c0 = (int64_t)k * per;
+    if (c0 >= n_cand) break;
+    const int64_t n = (c0 + per <= n_cand) ? per : n_cand - c0;
+    if (int rc = cuda_check(cudaMemcpyAsync(d_trees + c0 * kTreeBytes, h_trees + c0 * kTreeBytes, (size_t)n * kTreeBytes,
+                                            cudaMemcpyHostToDevice, P->h2d), "H2D trees")) return rc;
+    if (int rc = cuda_check(cudaEventRecord(P->copied[k], P->h2d), "cudaEventRecord")) return rc;
+    if (int rc = cuda_check(cudaStreamWaitEvent(st, P->copied[k], 0), "cudaStreamWaitEvent")) return rc;
+    if (int rc = launch_pairs(d_trees + c0 * kTreeBytes, n, grammar, d_eval_blob, n_eval, weights, variance, lengthscale,
+                              d_K + c0 * W.ld, nullptr, nullptr, W.ld, d_status + c0, d_recs + (size_t)c0 * kScanBytes,
+                              pairs_scratch_bytes(n), st)) return rc;
+    if (int rc = launch_posterior(d_K + c0 * W.ld, n, W.ld, n_eval, d_Linv, ldl, d_beta, mean_c, variance, acq_kind, d_current_max,
+                                  xi, ucb_beta, h_mu ? d_mu + c0 : nullptr, h_sigma ? d_sigma + c0 : nullptr,
+                                  h_acq ? d_acq + c0 : nullptr, st)) return rc;
+    if (int rc = cuda_check(cudaEventRecord(P->computed[k], st), "cudaEventRecord")) return rc;
+    if (int rc = cuda_check(cudaStreamWaitEvent(P->d2h, P->computed[k], 0), "cudaStreamWaitEvent")) return rc;
+    const size_t nb = sizeof(double) * (size_t)n;
+    if (h_mu) if (int rc = cuda_check(cudaMemcpyAsync(h_mu + c0, d_mu + c0, nb, cudaMemcpyDeviceToHost, P->d2h), "D2H mu")) return rc;
+    if (h_sigma) if (int rc = cuda_check(cudaMemcpyAsync(h_sigma + c0, d_sigma + c0, nb, cudaMemcpyDeviceToHost, P->d2h), "D2H sigma")) return rc;
+    if (h_acq) if (int rc = cuda_check(cudaMemcpyAsync(h_acq + c0, d_acq + c0, nb, cudaMemcpyDeviceToHost, P->d2h), "D2H acq")) return rc;
+  }
+  // join: the caller's stream completes only after the last D2H
+  if (int rc = cuda_check(cudaEventRecord(P->done, P->d2h), "cudaEventRecord")) return rc;
+  return cuda_check(cudaStreamWaitEvent(st, P->done, 0), "cudaStreamWaitEvent");
 }
