@@ -306,13 +306,21 @@ def main() -> None:
     else:  # posterior: K* panel read once, mu/sigma/EI written
         alg_bytes = (8.0 * N_EVAL + 24.0) * n_local
         dur = ms_post
+    traffic = None  # DRAM bytes per launch from the committed ncu capture, only when this run has the same shape
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("n_cand") == n_local and tj.get("n_eval") == N_EVAL and dominant in tj:
+            traffic = tj[dominant]["dram_bytes"]
     achieved = alg_bytes / (dur * 1e-3) / 1e9
     post_flops = n_local * (float(N_EVAL) * (N_EVAL + 1) + 4.0 * N_EVAL)  # triangular product + mean + norm
     roofline = dict(
         bound="hbm", kernel=dominant, achieved=achieved, peak=peaks["hbm_gbs"], unit="GB/s", frac=achieved / peaks["hbm_gbs"],
-        traffic=None, peak_source=peaks["source"],
+        traffic=traffic, peak_source=peaks["source"],
         algorithmic_bytes_per_launch=alg_bytes, kernel_ms=dur,
         kernels_ms=dict(sot_pair_kernel=ms_pairs, posterior_kernel=ms_post),
+        kernel_launches="sot_pair_kernel = scan_kernel + sot_pair_kernel (C-ABI bosot_sot_pairs); posterior_kernel = posterior_ws_kernel",
         note="fp64 issue, not HBM, is the practical ceiling of both kernels (DESIGN.md); secondary ceiling below",
         fp64=dict(measured_dfma_tflops=fp64_tflops, measured_dmma_tflops=dmma_tflops,
                   posterior_tflops=post_flops / (ms_post * 1e-3) / 1e12,
