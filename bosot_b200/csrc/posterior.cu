@@ -268,9 +268,10 @@ posterior_ws_kernel(PostParams p) {
         if (i >= 2) ws_mbar_wait(&empty[s], ((i >> 1) - 1) & 1);
         const int64_t c0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * TC;
         const int rows = (int)min((int64_t)TC, p.n_cand - c0);
-        ws_mbar_expect_tx(&full[s], (uint32_t)rows * (uint32_t)E * 8u);
+        const uint32_t row_bytes = (uint32_t)((E + 1) & ~1) * 8u;  // whole 16-byte units; for odd E one (finite) padding column comes along
+        ws_mbar_expect_tx(&full[s], (uint32_t)rows * row_bytes);
         double* dst = Ks + (size_t)s * TC * tld;
-        for (int c = 0; c < rows; ++c) ws_tma_g2s(dst + (size_t)c * tld, p.Kstar + (c0 + c) * p.ld, (uint32_t)E * 8u, &full[s]);
+        for (int c = 0; c < rows; ++c) ws_tma_g2s(dst + (size_t)c * tld, p.Kstar + (c0 + c) * p.ld, row_bytes, &full[s]);
       }
     }
     return;
@@ -520,7 +521,7 @@ int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_ev
   const size_t smem_cap = 226 * 1024;
 
   // warp-specialised TMA variant: needs 16-byte aligned rows of whole 16-byte units
-  const bool tma_ok = (n_eval % 2 == 0) && (ld % 2 == 0) && !(reinterpret_cast<uintptr_t>(d_Kstar) & 15);
+  const bool tma_ok = (ld % 2 == 0) && (n_eval % 2 == 0 || ld > n_eval) && !(reinterpret_cast<uintptr_t>(d_Kstar) & 15);
   if (tma_ok) {
     static bool ws_attr[64] = {false};
     if (!(dev < 64 && ws_attr[dev])) {
@@ -528,6 +529,8 @@ int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_ev
                               "cudaFuncSetAttribute(posterior_ws_kernel<64>)")) return rc;
       if (int rc = cuda_check(cudaFuncSetAttribute(posterior_ws_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
                               "cudaFuncSetAttribute(posterior_ws_kernel<32>)")) return rc;
+      if (int rc = cuda_check(cudaFuncSetAttribute(posterior_ws_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
+                              "cudaFuncSetAttribute(posterior_ws_kernel<16>)")) return rc;
       if (dev < 64) ws_attr[dev] = true;
     }
     const size_t s64 = ws_layout<64>(n_eval).total, s32 = ws_layout<32>(n_eval).total;
@@ -540,6 +543,12 @@ int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_ev
       const int64_t tiles = (n_cand + 31) / 32;
       posterior_ws_kernel<32><<<(unsigned)(tiles < sms ? tiles : sms), kWsThreads, s32, stream>>>(p);
       return after_launch("posterior_ws_kernel<32>");
+    }
+    const size_t s16 = ws_layout<16>(n_eval).total;
+    if (s16 <= smem_cap) {
+      const int64_t tiles = (n_cand + 15) / 16;
+      posterior_ws_kernel<16><<<(unsigned)(tiles < sms ? tiles : sms), kWsThreads, s16, stream>>>(p);
+      return after_launch("posterior_ws_kernel<16>");
     }
   }
 

@@ -395,6 +395,8 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
             if (p.D) p.D[row + e] = d;
           }
           if (p.K) p.K[row + e] = p.variance * exp_nonpos(d * p.neg_inv_lsq);
+        } else if (p.K && e < p.ld) {
+          p.K[row + e] = 0.0;  // padding columns of the Gram row stay finite (the posterior kernel may read them)
         }
       }
     }

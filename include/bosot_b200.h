@@ -150,6 +150,8 @@ int bosot_sot_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar*
  *   acq   = EI:  d*Phi(d/sigma) + sigma*phi(d/sigma),  d = mu - *d_current_max - xi
  *           UCB: mu + sqrt(ucb_beta)*sigma
  * d_current_max is a device scalar (ignored for UCB / NONE).  Any of mu/sigma/acq may be NULL.
+ * When ld > n_eval the padding columns [n_eval, ld) of K* must hold finite values (bosot_sot_pairs
+ * writes zeros there).  Supported n_eval: up to about 800 (shared-memory tiles).
  */
 #define BOSOT_ACQ_NONE 0
 #define BOSOT_ACQ_EI 1

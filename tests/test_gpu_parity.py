@@ -270,3 +270,40 @@ def test_full_size_properties(n_cand, n_eval):
     np.testing.assert_allclose(sigma[s_idx].cpu().numpy(), ref["sigma"], rtol=1e-6, atol=1e-12)
     np.testing.assert_allclose(ei[s_idx].cpu().numpy(), ref["acq"], rtol=1e-6, atol=1e-12)
     np.testing.assert_allclose(float(eng.current_max), ref["current_max"], rtol=1e-9)
+
+
+@pytest.mark.parametrize("n_eval", [300, 333, 600])
+def test_large_and_odd_evaluated_sets(n_eval):
+    """E beyond one register tile (256), odd E (TMA rows are padded to 16 bytes) and E that needs the smaller
+    posterior tiles: the device path against itself through independent routes plus the oracle on a sample."""
+    gen, d = "CKSHighDimSearchSpace", 5
+    gram = Grammar.get(gen, d)
+    ev_np, ca_np = random_stress_trees(n_eval, gram, seed=5), random_stress_trees(3000, gram, seed=6)
+    ca_np[7] = ev_np[n_eval - 1]
+    XE, XC = sot.as_device_trees(ev_np, DEV), sot.as_device_trees(ca_np, DEV)
+    hyp = rn.Hyper(**rn.H1)
+    w = hyp.alphas / hyp.alphas.sum()
+    y = np.random.default_rng(2).standard_normal(n_eval)
+    eng = sot.AcquisitionEngine(XE, torch.from_numpy(y), gram, w, hyp.variance, hyp.lengthscale, hyp.noise_variance, hyp.mean_c)
+    mu, sigma, ei = eng.acquire_device(XC)
+    # route 2: Gram from the pair kernel alone, posterior in torch fp64 (cuSOLVER / cuBLAS)
+    K = sot.sot_pairs(XC, eng.state, w, hyp.variance, hyp.lengthscale)["K"]
+    A = eng.K_EE + hyp.noise_variance * torch.eye(n_eval, dtype=torch.float64, device=DEV)
+    L = torch.linalg.cholesky(A)
+    V = torch.linalg.solve_triangular(L, K.t(), upper=False)
+    var = hyp.variance - (V * V).sum(0)
+    mean = K @ torch.cholesky_solve((torch.from_numpy(y).to(DEV) - hyp.mean_c).reshape(-1, 1), L)[:, 0] + hyp.mean_c
+    np.testing.assert_allclose(mu.cpu().numpy(), mean.cpu().numpy(), rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(sigma.cpu().numpy(), torch.sqrt(var).cpu().numpy(), rtol=1e-7, atol=1e-10)
+    assert float(K[7, n_eval - 1]) == hyp.variance
+    # oracle on a sample of rows
+    from bosot_b200.encoding import decode_to_tuple
+
+    idx = np.arange(0, 3000, 100)
+    ev_t = [decode_to_tuple(r, gram) for r in ev_np]
+    ca_t = [decode_to_tuple(ca_np[i], gram) for i in idx]
+    ref = rn.acquisition_function(ev_t, y, ca_t, hyp, gen, d)
+    np.testing.assert_allclose(K[torch.from_numpy(idx).to(DEV)].cpu().numpy(), rn.K(ca_t, ev_t, hyp, gen, d), rtol=1e-12)
+    np.testing.assert_allclose(mu.cpu().numpy()[idx], ref["mu"], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(sigma.cpu().numpy()[idx], ref["sigma"], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(ei.cpu().numpy()[idx], ref["acq"], rtol=1e-6, atol=1e-12)
