@@ -1,0 +1,154 @@
+"""Candidate production and the evolutionary acquisition optimiser directly on flat tree records
+(SURVEY.md 8f-2): the same moves, enumeration order and ``np.random`` consumption as the object API
+(``kernels/kernel_grammar/kernel_grammar_search_spaces.py`` / ``kernel_grammar_candidate_generator.py`` /
+``bayesian_optimization/evolutionary_optimizer_objects.py`` of the reference), without a Python object per
+expression: the population lives on the GPU as a uint8 ``[N, 64]`` tensor, offspring are produced by the
+``bosot_neighbours`` kernel, acquisition values by ``AcquisitionEngine.acquire_device``.  Neighbour numbers
+are drawn on the host with ``np.random`` exactly like the reference, so a seeded run visits the same kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .encoding import Grammar, decode_to_name
+
+
+def num_neighbours(trees: np.ndarray, n_symbols: int) -> np.ndarray:
+    """L*B + n*2*B per record (kernel_grammar_search_spaces.py:97-106), from the node-count byte alone."""
+    n = trees[:, 0].astype(np.int64)
+    return ((n + 1) // 2) * n_symbols + n * 2 * n_symbols
+
+
+def neighbour_at_index_host(record: np.ndarray, k: int, n_symbols: int) -> np.ndarray:
+    """Host restatement of ``get_neighbour_at_index`` on one flat record (used where the generation is
+    inherently sequential, and as the checker of the device kernel)."""
+    n = int(record[0])
+    toks = [int(t) for t in record[1 : 1 + n]]
+    L, B = (n + 1) // 2, n_symbols
+    if not (0 <= k < L * B + n * 2 * B):
+        raise IndexError("neighbour index out of range")
+    if k < L * B:
+        which, sym, seen = k // B, k % B, 0
+        for p, t in enumerate(toks):
+            if t < 0x80:
+                if seen == which:
+                    toks[p] = sym
+                seen += 1
+    else:
+        kk = k - L * B
+        node, op, sym = kk // (2 * B), (kk % (2 * B)) // B, kk % B
+        pending, end = 1, node
+        for p in range(node, n):
+            pending += 1 if toks[p] >= 0x80 else -1
+            if pending == 0:
+                end = p
+                break
+        toks = toks[:node] + [_lib.OP_ADD + op] + toks[node : end + 1] + [sym] + toks[end + 1 :]
+        if len(toks) > _lib.MAX_NODES:
+            raise ValueError("neighbour exceeds the %d-node flat record" % _lib.MAX_NODES)
+    out = np.full(_lib.TREE_BYTES, _lib.PAD, dtype=np.uint8)
+    out[0] = len(toks)
+    out[1 : 1 + len(toks)] = toks
+    return out
+
+
+def neighbours_device(trees: torch.Tensor, index: torch.Tensor, grammar: Grammar, check: bool = True) -> torch.Tensor:
+    """``out[i]`` = neighbour number ``index[i]`` of ``trees[i]`` (C-ABI ``bosot_neighbours``)."""
+    if not trees.is_cuda:
+        raise RuntimeError("bosot_b200: neighbours_device needs CUDA tensors (no CPU implementation on the product path)")
+    n = trees.shape[0]
+    out = torch.empty_like(trees)
+    status = torch.empty(n, dtype=torch.int32, device=trees.device)
+    index = index.to(trees.device, torch.int64).contiguous()
+    with torch.cuda.device(trees.device):
+        rc = _lib.load().bosot_neighbours(trees.data_ptr(), n, index.data_ptr(), grammar.n_symbols, out.data_ptr(), status.data_ptr(),
+                                          torch.cuda.current_stream(trees.device).cuda_stream)
+    _lib.check(rc, "neighbours")
+    if check:
+        bad = torch.nonzero(status)
+        if bad.numel():
+            i = int(bad[0])
+            raise ValueError("bosot_b200: neighbour move failed at row %d (code %d)" % (i, int(status[i])))
+    return out
+
+
+class FlatCandidateGenerator:
+    """Flat-record counterpart of ``KernelGrammarCandidateGenerator`` (reference
+    kernel_grammar_candidate_generator.py:27-117) for the two generators the EA uses."""
+
+    def __init__(self, grammar: Grammar):
+        self.grammar = grammar
+        B = grammar.n_symbols
+        self.roots = np.full((B, _lib.TREE_BYTES), _lib.PAD, dtype=np.uint8)
+        self.roots[:, 0] = 1
+        self.roots[:, 1] = np.arange(B)
+
+    def get_dataset_recursivly_generated(self, n_data: int, n_per_step: int = 1) -> np.ndarray:
+        """Roots first, then repeatedly a random neighbour of a randomly chosen earlier element
+        (:98-111).  Sequential by construction, so it runs on the host; ``np.random.choice`` is called
+        on an index range of the same length as the reference's list, which consumes the stream identically."""
+        B = self.grammar.n_symbols
+        pool = [r for r in self.roots]
+        while len(pool) < n_data:
+            chosen = pool[int(np.random.choice(len(pool)))]
+            for _ in range(n_per_step):
+                if len(pool) < n_data:
+                    k = int(np.random.choice(int(num_neighbours(chosen[None, :], B)[0])))
+                    pool.append(neighbour_at_index_host(chosen, k, B))
+        return np.stack(pool[:max(n_data, B)])
+
+    def get_initial_for_evolutionary_opt(self, n_initial: int) -> np.ndarray:
+        return self.get_dataset_recursivly_generated(n_initial, 1)
+
+    def draw_offspring_indices(self, survivors: np.ndarray, n_around: int) -> Tuple[np.ndarray, np.ndarray]:
+        """(parent row, neighbour number) for ``n_around`` random neighbours of every survivor, drawn in the
+        reference's order (survivor-major, :85-93)."""
+        counts = num_neighbours(survivors, self.grammar.n_symbols)
+        parent = np.repeat(np.arange(len(survivors)), n_around)
+        index = np.array([int(np.random.choice(int(counts[p]))) for p in parent], dtype=np.int64)
+        return parent, index
+
+
+class FlatEvolutionaryOptimizer:
+    """``EvolutionaryOptimizerObjects`` (reference evolutionary_optimizer_objects.py:24-71) on flat records:
+    select the top ``pop / (offspring + 1)`` by acquisition value, every survivor spawns ``offspring`` random
+    neighbours, new population = offspring + survivors; the best individual ever seen is returned."""
+
+    def __init__(self, population_size: int, num_offspring: int, generator: FlatCandidateGenerator, device: Optional[torch.device] = None):
+        self.population_size = population_size
+        self.num_offspring = num_offspring
+        self.generator = generator
+        self.survival_rate = 1 / (num_offspring + 1)
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.current_maximizer: Optional[np.ndarray] = None
+        self.current_maximizer_value = -np.inf
+
+    def maximize(self, func: Callable[[torch.Tensor], torch.Tensor], steps: int):
+        """``func`` maps a device tensor of flat records to a device tensor of acquisition values."""
+        gen = self.generator
+        population = torch.from_numpy(gen.get_initial_for_evolutionary_opt(self.population_size)).to(self.device)
+        values = None
+        for step in range(steps):
+            if step > 0:
+                order = np.argsort(values)  # host argsort: the reference's tie-breaking, 8 bytes per candidate
+                n_survive = int(self.population_size * self.survival_rate)
+                surv_idx = order[len(order) - n_survive:]
+                survivors = population[torch.from_numpy(surv_idx).to(self.device)]
+                parent, index = gen.draw_offspring_indices(survivors.cpu().numpy(), self.num_offspring)
+                offspring = neighbours_device(survivors[torch.from_numpy(parent).to(self.device)].contiguous(),
+                                              torch.from_numpy(index), gen.grammar)
+                population = torch.cat([offspring, survivors])
+            values = func(population).cpu().numpy()
+            fittest = int(np.argmax(values))
+            if self.current_maximizer_value < values[fittest]:
+                self.current_maximizer_value = float(values[fittest])
+                self.current_maximizer = population[fittest].cpu().numpy()
+        return self.current_maximizer, self.current_maximizer_value
+
+    def best_name(self) -> str:
+        return decode_to_name(self.current_maximizer, self.generator.grammar)

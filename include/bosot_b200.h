@@ -103,6 +103,8 @@ int bosot_abi_version(void);
 #define BOSOT_TREE_BAD_LENGTH 1
 #define BOSOT_TREE_BAD_TOKEN 2
 #define BOSOT_TREE_BAD_SHAPE 3
+#define BOSOT_NEIGHBOUR_BAD_INDEX 4
+#define BOSOT_NEIGHBOUR_TOO_BIG 5 /* the move would exceed 63 nodes */
 
 int bosot_featurize(const uint8_t* d_trees, int64_t n_trees, const bosot_grammar* grammar,
                     uint8_t* d_n_nodes, uint8_t* d_n_leaves,
@@ -190,6 +192,15 @@ int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, const bosot_gra
                          int acq_kind, const double* d_current_max, double xi, double ucb_beta,
                          void* d_work, size_t work_bytes,
                          double* d_mu, double* d_sigma, double* d_acq, void* stream);
+
+/* ---- candidate production on the flat encoding --------------------------------
+ * bosot_neighbours: out[i] = neighbour number index[i] of trees[i] in the enumeration of
+ * BaseKernelGrammarSearchSpace.get_neighbour_at_index (kernel_grammar_search_spaces.py:108-142):
+ * a tree with L leaves and n nodes has L*B + 2*n*B neighbours (leaf swaps first, then extensions of
+ * every sub-expression, root first, by (ADD | MULTIPLY, base kernel)).  d_status (may be NULL): 0 or a
+ * BOSOT_TREE_* / BOSOT_NEIGHBOUR_* code; on error the input tree is copied through unchanged. */
+int bosot_neighbours(const uint8_t* d_trees, int64_t n_trees, const int64_t* d_index, int n_symbols,
+                     uint8_t* d_out, int32_t* d_status, void* stream);
 
 /* ---- measurement helpers -----------------------------------------------------------------
  * bosot_fp64_fma_probe / bosot_fp64_mma_probe: run `iters` x 8 independent DFMA (resp. fp64

@@ -1,0 +1,94 @@
+"""Candidate production on the flat encoding: host restatement vs the object API (CPU),
+device kernel vs host restatement and the flat EA vs the object EA (GPU)."""
+import numpy as np
+import pytest
+
+from bosot_b200.configs.kernels.kernel_grammar_generators.generator_configs import CKSHighDimGeneratorConfig, CKSWithRQGeneratorConfig
+from bosot_b200.encoding import Grammar, decode_to_name, encode, random_stress_trees
+from bosot_b200.flat_search import FlatCandidateGenerator, neighbour_at_index_host, num_neighbours
+from bosot_b200.kernels.kernel_grammar.generator_factory import GeneratorFactory
+
+
+@pytest.mark.parametrize("cfg,d", [(CKSWithRQGeneratorConfig, 2), (CKSHighDimGeneratorConfig, 3)])
+def test_host_moves_match_object_api(cfg, d):
+    gen = GeneratorFactory.build(cfg(input_dimension=d))
+    ss = gen.search_space
+    gram = Grammar.get(ss.name, d)
+    np.random.seed(9)
+    exprs = gen.get_dataset_recursivly_generated(40, 1)[::3]
+    flat = encode(exprs, gram)
+    counts = num_neighbours(flat, gram.n_symbols)
+    for e, rec, cnt in zip(exprs, flat, counts):
+        assert cnt == ss.get_num_neighbour_expressions(e)
+        for k in list(range(0, cnt, max(1, cnt // 17))) + [cnt - 1]:
+            assert decode_to_name(neighbour_at_index_host(rec, k, gram.n_symbols), gram) == str(ss.get_neighbour_at_index(e, k))
+    with pytest.raises(IndexError):
+        neighbour_at_index_host(flat[0], int(counts[0]), gram.n_symbols)
+
+
+def test_flat_generator_consumes_rng_like_object_generator():
+    gen = GeneratorFactory.build(CKSWithRQGeneratorConfig(input_dimension=2))
+    gram = Grammar.get("CKSWithRQSearchSpace", 2)
+    np.random.seed(3)
+    names = [str(x) for x in gen.get_dataset_recursivly_generated(100, 1)]
+    after_obj = np.random.random()
+    np.random.seed(3)
+    flat = FlatCandidateGenerator(gram).get_dataset_recursivly_generated(100, 1)
+    after_flat = np.random.random()
+    assert [decode_to_name(r, gram) for r in flat] == names and after_obj == after_flat
+
+
+@pytest.mark.gpu
+def test_device_moves_match_host():
+    torch = pytest.importorskip("torch")
+    from bosot_b200 import sot
+    from bosot_b200.flat_search import neighbours_device
+
+    gram = Grammar.get("CKSHighDimSearchSpace", 5)
+    trees = random_stress_trees(3000, gram, seed=21, max_depth=4)
+    rng = np.random.default_rng(0)
+    counts = num_neighbours(trees, gram.n_symbols)
+    index = (rng.random(len(trees)) * counts).astype(np.int64)
+    index[:4] = [0, counts[1] - 1, (trees[2, 0] + 1) // 2 * gram.n_symbols, (trees[3, 0] + 1) // 2 * gram.n_symbols - 1]
+    out = neighbours_device(sot.as_device_trees(trees, "cuda:0"), torch.from_numpy(index), gram).cpu().numpy()
+    ref = np.stack([neighbour_at_index_host(r, int(k), gram.n_symbols) for r, k in zip(trees, index)])
+    assert np.array_equal(out, ref)
+    # errors: index out of range, tree that would outgrow the record
+    big = random_stress_trees(2000, gram, seed=5)
+    full = big[big[:, 0] == 63][:1]
+    if len(full):
+        with pytest.raises(ValueError, match="code 5"):
+            neighbours_device(sot.as_device_trees(full, "cuda:0"), torch.tensor([32 * gram.n_symbols]), gram)
+    with pytest.raises(ValueError, match="code 4"):
+        neighbours_device(sot.as_device_trees(trees[:1], "cuda:0"), torch.tensor([int(counts[0])]), gram)
+
+
+@pytest.mark.gpu
+def test_flat_ea_visits_the_same_kernels_as_the_object_ea():
+    torch = pytest.importorskip("torch")
+    from bosot_b200 import _lib, sot
+    from bosot_b200.bayesian_optimization.evolutionary_optimizer_objects import EvolutionaryOptimizerObjects
+    from bosot_b200.flat_search import FlatEvolutionaryOptimizer
+    from bosot_b200.oracles.structural_oracle import StructuralOracle
+
+    d, space = 2, "CKSWithRQSearchSpace"
+    gram = Grammar.get(space, d)
+    gen = GeneratorFactory.build(CKSWithRQGeneratorConfig(input_dimension=d))
+    oracle = StructuralOracle(gram.symbols, seed=3)
+    np.random.seed(1)
+    x = gen.get_random_canditates(16)
+    y = np.array([oracle.query(e)[0] for e in x])
+    dev = torch.device("cuda:0")
+    eng = sot.AcquisitionEngine(sot.as_device_trees(encode(x, gram), dev), torch.from_numpy(y), gram, (0.3, 0.3, 0.4), 1.3, 0.8, 1e-3, -0.5,
+                                acq_kind=_lib.ACQ_UCB)
+
+    def acq_objects(pop):
+        return eng.acquire_device(sot.as_device_trees(encode(pop, gram), dev))[2].cpu().numpy()
+
+    np.random.seed(77)
+    best_obj, val_obj = EvolutionaryOptimizerObjects(60, 4, gen).maximize(acq_objects, 4)
+    np.random.seed(77)
+    flat_ea = FlatEvolutionaryOptimizer(60, 4, FlatCandidateGenerator(gram), dev)
+    best_flat, val_flat = flat_ea.maximize(lambda t: eng.acquire_device(t)[2], 4)
+    assert flat_ea.best_name() == str(best_obj)
+    assert val_flat == float(val_obj)
