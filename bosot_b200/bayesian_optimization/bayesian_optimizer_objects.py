@@ -57,6 +57,9 @@ class BayesianOptimizerObjects:
         self.oracle = None
         self.gp_ucb_beta = 3.0
         self.ei_xi = 0.01
+        # EA on flat records (GPU population, same np.random consumption => same proposals as the object EA);
+        # switched off automatically when the set-up is not the plain kernel-grammar one
+        self.use_flat_evolutionary = True
 
     # ---- wiring -----------------------------------------------------------------------------
     def set_oracle(self, oracle):
@@ -102,9 +105,34 @@ class BayesianOptimizerObjects:
         if self.acquisiton_optimization_type == AcquisitionOptimizationObjectBOType.TRAILING_CANDIDATES:
             acquisition_values = self.acquisition_function(self.candidates)
             return self.candidates[int(np.argmax(acquisition_values))], acquisition_values
+        if self._flat_evolutionary_possible():
+            return self._update_flat_evolutionary(), None
         optimizer = EvolutionaryOptimizerObjects(self.population_evolutionary, self.num_offspring_evolutionary, self.candidate_generator)
         new_query, _ = optimizer.maximize(self.acquisition_function, self.n_steps_evolutionary)
         return new_query, None
+
+    def _flat_evolutionary_possible(self) -> bool:
+        return (
+            self.use_flat_evolutionary
+            and hasattr(self.candidate_generator, "search_space")
+            and self.model.prediction_quantity == PredictionQuantity.PREDICT_F
+            and not getattr(self.model.kernel, "transform_to_normal", False)
+            and self.acquisition_function_type in (AcquisitionFunctionType.GP_UCB, AcquisitionFunctionType.EXPECTED_IMPROVEMENT)
+        )
+
+    def _update_flat_evolutionary(self):
+        """The EA of `update` with the whole population resident on the GPU as flat records: no Python
+        object per candidate, acquisition values straight from the fused device pass."""
+        from ..encoding import Grammar
+        from ..flat_search import FlatCandidateGenerator, FlatEvolutionaryOptimizer, record_to_expression
+
+        space = self.candidate_generator.search_space
+        grammar = Grammar.get(space.name, space.input_dimension)
+        acq_kind = _lib.ACQ_UCB if self.acquisition_function_type == AcquisitionFunctionType.GP_UCB else _lib.ACQ_EI
+        engine = self.model.engine(acq_kind=acq_kind, xi=self.ei_xi, ucb_beta=self.gp_ucb_beta)
+        ea = FlatEvolutionaryOptimizer(self.population_evolutionary, self.num_offspring_evolutionary, FlatCandidateGenerator(grammar), engine.device)
+        best, _ = ea.maximize(lambda trees: engine.acquire_device(trees)[2], self.n_steps_evolutionary)
+        return record_to_expression(best, space)
 
     def acquisition_function(self, x_grid: List[object]) -> np.ndarray:
         """EI / GP-UCB / EI-per-second for every candidate (BOO:159-178), numpy fp64 [N]."""

@@ -152,3 +152,23 @@ class FlatEvolutionaryOptimizer:
 
     def best_name(self) -> str:
         return decode_to_name(self.current_maximizer, self.generator.grammar)
+
+
+def record_to_expression(record: np.ndarray, search_space):
+    """Flat record -> expression objects of the mirror API (leaves built through the search space's own
+    base-kernel configs, ``generator_name`` set like the reference's neighbour constructors do)."""
+    from .encoding import decode_to_tuple
+    from .kernels.kernel_factory import KernelFactory
+    from .kernels.kernel_grammar.kernel_grammar import ElementaryKernelGrammarExpression, KernelGrammarExpression, KernelGrammarOperator
+
+    grammar = Grammar.get(search_space.name, search_space.input_dimension)
+
+    def build(t):
+        if isinstance(t, str):
+            e = ElementaryKernelGrammarExpression(KernelFactory.build(search_space.base_kernel_config_list[grammar.symbol_index[t]]))
+        else:
+            e = KernelGrammarExpression(build(t[1]), build(t[2]), KernelGrammarOperator[t[0]])
+        e.set_generator_name(search_space.name)
+        return e
+
+    return build(decode_to_tuple(record, grammar))

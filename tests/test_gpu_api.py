@@ -233,6 +233,7 @@ def test_bo_loop_makes_the_same_selections_as_the_cpu_path():
 
     gen = GeneratorFactory.build(CKSWithRQGeneratorConfig(input_dimension=d))
     bo = _CheckedBO(hyp, space, d, **ObjectBOExpectedImprovementEAConfig(n_steps_evolutionary=3, population_evolutionary=50).dict())
+    bo.use_flat_evolutionary = False  # the object EA calls acquisition_function, which is what this run cross-checks
     bo.set_model(_toy_model(hyp, d))
     bo.set_oracle(StructuralOracle([str(r) for r in gen.search_space.get_root_expressions()], seed=3))
     bo.set_candidate_generator(gen)
@@ -240,3 +241,24 @@ def test_bo_loop_makes_the_same_selections_as_the_cpu_path():
     bo.sample_train_set(16)
     metrics, queries, *_ = bo.maximize(5)
     assert bo.calls == 15 and bo.same_argmax >= 13 and len(queries) == 5
+
+
+def test_flat_and_object_evolutionary_modes_agree():
+    """BayesianOptimizerObjects proposes the same queries whether its EA runs on expression objects or on
+    flat records resident on the GPU (same np.random consumption, same acquisition values)."""
+    d = 2
+    hyp = rn.Hyper(alphas=(0.4, 0.4, 0.4), lengthscale=0.8, variance=1.3, noise_variance=1e-3, mean_c=-0.5)
+    runs = []
+    for flat in (True, False):
+        gen = GeneratorFactory.build(CKSWithRQGeneratorConfig(input_dimension=d))
+        bo = BayesianOptimizerObjects(**ObjectBOExpectedImprovementEAConfig(n_steps_evolutionary=3, population_evolutionary=50).dict())
+        bo.use_flat_evolutionary = flat
+        bo.set_model(_toy_model(hyp, d))
+        bo.set_oracle(StructuralOracle([str(r) for r in gen.search_space.get_root_expressions()], seed=3))
+        bo.set_candidate_generator(gen)
+        np.random.seed(42)
+        bo.sample_train_set(16)
+        _, queries, *_ = bo.maximize(4)
+        runs.append([str(q) for q, _ in queries])
+        assert all(q.get_generator_name() == "CKSWithRQSearchSpace" for q, _ in queries)
+    assert runs[0] == runs[1], runs
