@@ -70,6 +70,8 @@ SIGNATURES = {
          _P, C.c_size_t, _P, _P, _P, _P],
     ),
     "bosot_neighbours": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P, _P]),
+    "bosot_gp_fit_max_eval": (C.c_int, []),
+    "bosot_gp_nll_grad": (C.c_int, [_P, C.c_int, C.c_int64, _P, _D3, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P]),
     "bosot_fp64_fma_probe": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "bosot_fp64_mma_probe": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "bosot_fp64_mma_probe2": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),

@@ -1,0 +1,204 @@
+// GP-over-kernels marginal likelihood and its analytic gradient in ONE launch.
+//
+// What the reference evaluates through GPflow/TF autodiff on every L-BFGS step of the hyper-parameter
+// fit (bosot/models/gp_model.py:162-199 -> GPR.training_loss = -log_marginal_likelihood):
+//     K    = var * exp(-D / ls^2) + noise * I,   D = sum_f w_f * Df[f]      (kernel_kernel_grammar_tree.py:110-113,159-161)
+//     loss = 0.5 r^T K^-1 r + sum_i log L_ii + 0.5 E log(2 pi),  r = y - c,  K = L L^T
+//     dloss/dtheta = 0.5 * sum_ij (Kinv_ij - alpha_i alpha_j) dK_ij/dtheta,  alpha = K^-1 r
+// The three E x E per-feature distance matrices Df are constants of the fit (they come from the pair
+// kernel once per model update), E is small (tens to ~150), so the whole evaluation is one CTA:
+// Cholesky in shared memory, two triangular solves, L^-1 written into the unused upper triangle,
+// and Kinv_ij formed on the fly as row dot products while the five weighted sums are accumulated.
+// Gradients are returned with respect to the CONSTRAINED quantities (w_f treated as independent, ls,
+// var, noise, c); the host applies the chain rule of the sigmoid / softplus transforms.
+#include "sot_common.cuh"
+#include "launch.cuh"
+
+namespace bosot {
+
+constexpr int kFitThreads = 256;
+constexpr int kFitMaxE = 160;
+
+struct FitParams {
+  const double* Df;  // [3][E][ld]
+  int E;
+  int64_t ld;
+  const double* y;   // [E]
+  double w[3], ls, var, noise, c;
+  double* out;       // [0] loss, [1..3] dL/dw_f, [4] dL/dls, [5] dL/dvar, [6] dL/dnoise, [7] dL/dc, [8] info (0 ok, k+1 = minor k not PD)
+};
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < kFitThreads / 32; ++w) s += red[w];  // fixed order: reproducible
+  return s;
+}
+
+__global__ void __launch_bounds__(kFitThreads)
+gp_nll_grad_kernel(FitParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int E = p.E, lda = E | 1;
+  double* A = reinterpret_cast<double*>(smem);  // [E][lda]: lower = L, strict upper = (L^-1)^T
+  double* r = A + (size_t)E * lda;              // residual, then forward-solve result
+  double* alpha = r + E;
+  double* dinv = alpha + E;                     // diagonal of L^-1
+  double* red = dinv + E;                       // [8]
+  __shared__ int s_info;
+  const int tid = threadIdx.x;
+  const double inv_ls2 = 1.0 / (p.ls * p.ls);
+  const size_t plane = (size_t)E * p.ld;
+  if (tid == 0) s_info = 0;
+
+  // K (lower triangle) and the residual
+  for (int idx = tid; idx < E * E; idx += kFitThreads) {
+    const int i = idx / E, j = idx - i * E;
+    if (j <= i) {
+      const size_t o = (size_t)i * p.ld + j;
+      const double D = p.w[0] * p.Df[o] + p.w[1] * p.Df[plane + o] + p.w[2] * p.Df[2 * plane + o];
+      A[i * lda + j] = p.var * exp(-D * inv_ls2) + (i == j ? p.noise : 0.0);
+    }
+  }
+  for (int i = tid; i < E; i += kFitThreads) r[i] = p.y[i] - p.c;
+  __syncthreads();
+
+  // Cholesky, right-looking
+  for (int k = 0; k < E; ++k) {
+    if (tid == 0) {
+      const double a = A[k * lda + k];
+      if (!(a > 0.0) && s_info == 0) s_info = k + 1;
+      A[k * lda + k] = sqrt(a);
+    }
+    __syncthreads();
+    const double piv = A[k * lda + k];
+    for (int i = k + 1 + tid; i < E; i += kFitThreads) A[i * lda + k] /= piv;
+    __syncthreads();
+    const int n = E - k - 1;
+    for (int idx = tid; idx < n * n; idx += kFitThreads) {
+      const int a = idx / n, b = idx - a * n;
+      if (b <= a) {
+        const int i = k + 1 + a, j = k + 1 + b;
+        A[i * lda + j] -= A[i * lda + k] * A[j * lda + k];
+      }
+    }
+    __syncthreads();
+  }
+  if (s_info != 0) {  // not positive definite: report like a failed Cholesky, the caller retries
+    if (tid == 0) {
+      const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+      for (int q = 0; q < 8; ++q) p.out[q] = qnan;
+      p.out[8] = (double)s_info;
+    }
+    return;
+  }
+
+  // alpha = K^-1 r : forward then backward substitution (column sweeps)
+  for (int k = 0; k < E; ++k) {
+    if (tid == 0) r[k] /= A[k * lda + k];
+    __syncthreads();
+    const double zk = r[k];
+    for (int i = k + 1 + tid; i < E; i += kFitThreads) r[i] -= A[i * lda + k] * zk;
+    __syncthreads();
+  }
+  double quad = 0.0, logdet = 0.0;
+  for (int i = tid; i < E; i += kFitThreads) { quad += r[i] * r[i]; logdet += log(A[i * lda + i]); }
+  quad = block_sum(quad, red);
+  logdet = block_sum(logdet, red);
+  for (int i = tid; i < E; i += kFitThreads) alpha[i] = r[i];
+  __syncthreads();
+  for (int k = E - 1; k >= 0; --k) {
+    if (tid == 0) alpha[k] /= A[k * lda + k];
+    __syncthreads();
+    const double ak = alpha[k];
+    for (int i = tid; i < k; i += kFitThreads) alpha[i] -= A[k * lda + i] * ak;
+    __syncthreads();
+  }
+
+  // L^-1, one thread per column j, written transposed into the strict upper triangle: A[j][i] = Linv[i][j], i > j
+  for (int j = tid; j < E; j += kFitThreads) {
+    const double dj = 1.0 / A[j * lda + j];
+    dinv[j] = dj;
+    for (int i = j + 1; i < E; ++i) {
+      double s = A[i * lda + j] * dj;  // k = j term
+      for (int k = j + 1; k < i; ++k) s += A[i * lda + k] * A[j * lda + k];
+      A[j * lda + i] = -s / A[i * lda + i];
+    }
+  }
+  __syncthreads();
+
+  // Kinv_ij = sum_{k >= i} U[i][k] U[j][k] (i >= j), U = (L^-1)^T upper triangular (diag in dinv); weighted sums
+  double s_var = 0.0, s_f0 = 0.0, s_f1 = 0.0, s_f2 = 0.0, s_noise = 0.0;
+  const int n_pairs = E * (E + 1) / 2;
+  for (int idx = tid; idx < n_pairs; idx += kFitThreads) {
+    // idx -> (i, j), j <= i, row-major over the lower triangle
+    int i = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= idx) ++i;
+    while (i * (i + 1) / 2 > idx) --i;
+    const int j = idx - i * (i + 1) / 2;
+    const double* ui = A + (size_t)i * lda;
+    const double* uj = A + (size_t)j * lda;
+    double kinv = dinv[i] * (i == j ? dinv[i] : uj[i]);
+    for (int k = i + 1; k < E; ++k) kinv += ui[k] * uj[k];
+    const double q = kinv - alpha[i] * alpha[j];
+    const size_t o = (size_t)i * p.ld + j;
+    const double d0 = p.Df[o], d1 = p.Df[plane + o], d2 = p.Df[2 * plane + o];
+    const double G = exp(-(p.w[0] * d0 + p.w[1] * d1 + p.w[2] * d2) * inv_ls2);
+    const double qg = (i == j ? 1.0 : 2.0) * q * G;  // symmetric: every off-diagonal pair counts twice
+    s_var += qg;
+    s_f0 += qg * d0;
+    s_f1 += qg * d1;
+    s_f2 += qg * d2;
+    if (i == j) s_noise += q;
+  }
+  s_var = block_sum(s_var, red);
+  s_f0 = block_sum(s_f0, red);
+  s_f1 = block_sum(s_f1, red);
+  s_f2 = block_sum(s_f2, red);
+  s_noise = block_sum(s_noise, red);
+  double s_alpha = 0.0;
+  for (int i = tid; i < E; i += kFitThreads) s_alpha += alpha[i];
+  s_alpha = block_sum(s_alpha, red);
+
+  if (tid == 0) {
+    p.out[0] = 0.5 * quad + logdet + 0.5 * E * 1.8378770664093454836;  // log(2 pi)
+    const double cf = -0.5 * p.var * inv_ls2;                          // dK/dw_f = -var/ls^2 * G * Df[f]
+    p.out[1] = cf * s_f0;
+    p.out[2] = cf * s_f1;
+    p.out[3] = cf * s_f2;
+    p.out[4] = p.var / (p.ls * p.ls * p.ls) * (p.w[0] * s_f0 + p.w[1] * s_f1 + p.w[2] * s_f2);  // 0.5 * sum q * var G D * 2/ls^3
+    p.out[5] = 0.5 * s_var;
+    p.out[6] = 0.5 * s_noise;
+    p.out[7] = -s_alpha;
+    p.out[8] = 0.0;
+  }
+}
+
+}  // namespace bosot
+
+extern "C" int bosot_gp_fit_max_eval(void) { return bosot::kFitMaxE; }
+
+extern "C" int bosot_gp_nll_grad(const double* d_Df, int n_eval, int64_t ld, const double* d_y, const double weights[3],
+                                 double lengthscale, double variance, double noise_variance, double mean_c,
+                                 double* d_out9, void* stream) {
+  using namespace bosot;
+  if (!d_Df || !d_y || !weights || !d_out9) return set_error(BOSOT_EINVAL, "bosot_gp_nll_grad: null argument");
+  if (n_eval < 1 || n_eval > kFitMaxE || ld < n_eval) return set_error(BOSOT_EINVAL, "bosot_gp_nll_grad: n_eval out of range (see bosot_gp_fit_max_eval)");
+  FitParams p;
+  p.Df = d_Df; p.E = n_eval; p.ld = ld; p.y = d_y;
+  p.w[0] = weights[0]; p.w[1] = weights[1]; p.w[2] = weights[2];
+  p.ls = lengthscale; p.var = variance; p.noise = noise_variance; p.c = mean_c; p.out = d_out9;
+  const size_t smem = sizeof(double) * ((size_t)n_eval * (n_eval | 1) + 3 * (size_t)n_eval + 8);
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(dev < 64 && attr_set[dev])) {
+    if (int rc = cuda_check(cudaFuncSetAttribute(gp_nll_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024),
+                            "cudaFuncSetAttribute(gp_nll_grad_kernel)")) return rc;
+    if (dev < 64) attr_set[dev] = true;
+  }
+  gp_nll_grad_kernel<<<1, kFitThreads, smem, (cudaStream_t)stream>>>(p);
+  return after_launch("gp_nll_grad_kernel");
+}

@@ -80,6 +80,7 @@ class ObjectGpModel:
         self.likelihood_variance = Parameter(np.power(observation_noise, 2.0), trainable=train_likelihood_variance)
         self._engine = None
         self.print_summaries = True
+        self.use_fused_fit = True  # bosot_gp_nll_grad; False = torch autograd (the checker / large-E path)
 
     # ------------------------------------------------------------------ small helpers
     def _kernel_parameters(self) -> List[Parameter]:
@@ -166,8 +167,66 @@ class ObjectGpModel:
             p.assign(from_u(new_u))
 
     def _loss_and_grad(self, theta: np.ndarray, layout) -> Tuple[float, np.ndarray]:
-        """Negative log marginal likelihood of GPR (+ the exponential prior on the noise when asked)
-        and its gradient in unconstrained space: torch fp64 autograd on the device holding D_f."""
+        """Negative log marginal likelihood of GPR (+ the exponential prior on the noise when asked) and its
+        gradient in unconstrained space.  Fused CUDA kernel (``bosot_gp_nll_grad``: one launch per evaluation,
+        analytic gradient) when the evaluated set fits its shared-memory Cholesky, else torch fp64 autograd."""
+        Df = self.model["Df"]
+        if self.use_fused_fit and Df.is_cuda and Df.shape[1] <= _lib.load().bosot_gp_fit_max_eval():
+            return self._loss_and_grad_fused(theta, layout)
+        return self._loss_and_grad_autograd(theta, layout)
+
+    def _loss_and_grad_fused(self, theta: np.ndarray, layout) -> Tuple[float, np.ndarray]:
+        import ctypes as C
+
+        k = self.kernel
+        vals, pos = {}, 0
+        for name, n in layout:
+            vals[name] = np.asarray(theta[pos : pos + n], dtype=np.float64)
+            pos += n
+        sig = lambda u: 1.0 / (1.0 + np.exp(-u))  # noqa: E731
+        alphas = sig(vals["alphas"]) if "alphas" in vals else np.asarray(k.alphas.numpy(), dtype=np.float64)
+        ls = float(_softplus(vals["lengthscale"])[0]) if "lengthscale" in vals else float(k.lengthscale)
+        var = float(_softplus(vals["variance"])[0]) if "variance" in vals else float(k.variance)
+        lo = LIKELIHOOD_VARIANCE_LOWER_BOUND
+        noise = float(_softplus(vals["noise"])[0]) + lo if "noise" in vals else float(self.likelihood_variance)
+        c = float(vals["c"][0]) if "c" in vals else self.mean_function.value()
+        S = float(np.sum(alphas))
+        order = [_DEVICE_ORDER.index(f) for f in k.feature_type_list]
+        w3 = np.zeros(3)
+        for g, a in zip(order, alphas):
+            w3[g] += a / S
+        Df, y = self.model["Df"], self.model["y"]
+        if getattr(self, "_fit_out", None) is None or self._fit_out.device != Df.device:
+            self._fit_out = torch.empty(9, dtype=torch.float64, device=Df.device)
+        with torch.cuda.device(Df.device):
+            rc = _lib.load().bosot_gp_nll_grad(Df.data_ptr(), Df.shape[1], Df.stride(1), y.data_ptr(), (C.c_double * 3)(*w3), ls, var, noise, c,
+                                               self._fit_out.data_ptr(), torch.cuda.current_stream(Df.device).cuda_stream)
+        _lib.check(rc, "gp_nll_grad")
+        out = self._fit_out.cpu().numpy()
+        if out[8] != 0.0:
+            raise RuntimeError("Cholesky decomposition was not successful (leading minor %d not positive definite)" % int(out[8]))
+        loss = float(out[0])
+        d_w3, d_ls, d_var, d_noise, d_c = out[1:4], out[4], out[5], out[6], out[7]
+        if self.set_prior_on_observation_noise:  # tfd.Exponential(rate) log-density on the constrained value
+            rate = 1.0 / np.power(self.expected_observation_noise, 2.0)
+            loss -= np.log(rate) - rate * noise
+            d_noise = d_noise + rate
+        grads = []
+        for name, n in layout:
+            if name == "alphas":  # w_g = alpha_g / S, alpha = sigmoid(u)
+                d_alpha = (np.array([d_w3[g] for g in order]) - float(np.dot(d_w3, w3))) / S
+                grads.append(d_alpha * alphas * (1.0 - alphas))
+            elif name == "lengthscale":
+                grads.append(np.array([d_ls * (1.0 - np.exp(-ls))]))
+            elif name == "variance":
+                grads.append(np.array([d_var * (1.0 - np.exp(-var))]))
+            elif name == "noise":
+                grads.append(np.array([d_noise * (1.0 - np.exp(-(noise - lo)))]))
+            else:
+                grads.append(np.array([d_c]))
+        return loss, (np.concatenate(grads) if grads else np.zeros(0))
+
+    def _loss_and_grad_autograd(self, theta: np.ndarray, layout) -> Tuple[float, np.ndarray]:
         dev = self.model["Df"].device
         t = torch.tensor(theta, dtype=torch.float64, device=dev, requires_grad=True)
         vals = {}

@@ -193,6 +193,19 @@ int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, const bosot_gra
                          void* d_work, size_t work_bytes,
                          double* d_mu, double* d_sigma, double* d_acq, void* stream);
 
+/* ---- hyper-parameter fit of the GP over kernels ----------------------------------
+ * One launch = one evaluation of GPR's training loss (negative log marginal likelihood; reference
+ * bosot/models/gp_model.py:195-199) and its analytic gradient, for K = variance*exp(-D/ls^2) + noise*I,
+ * D = sum_f weights[f]*Df[f], residual y - mean_c.  d_Df: [3][n_eval][ld] per-feature distance matrices of
+ * the evaluated set (bosot_sot_pairs with d_Df), constants of the fit.  d_out9: [0] loss, [1..3] dloss/dw_f
+ * (weights treated as independent), [4] dloss/dlengthscale, [5] dloss/dvariance, [6] dloss/dnoise,
+ * [7] dloss/dmean_c, [8] info (0, or k+1 when the leading minor k is not positive definite: then [0..7] = NaN).
+ * Single CTA, matrices in shared memory: n_eval <= bosot_gp_fit_max_eval(). */
+int bosot_gp_fit_max_eval(void);
+int bosot_gp_nll_grad(const double* d_Df, int n_eval, int64_t ld, const double* d_y, const double weights[3],
+                      double lengthscale, double variance, double noise_variance, double mean_c,
+                      double* d_out9, void* stream);
+
 /* ---- candidate production on the flat encoding --------------------------------
  * bosot_neighbours: out[i] = neighbour number index[i] of trees[i] in the enumeration of
  * BaseKernelGrammarSearchSpace.get_neighbour_at_index (kernel_grammar_search_spaces.py:108-142):

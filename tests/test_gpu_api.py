@@ -135,6 +135,21 @@ def test_marginal_likelihood_and_gradient():
         e[i] = 1e-5
         num = (model._loss_and_grad(theta + e, layout)[0] - model._loss_and_grad(theta - e, layout)[0]) / 2e-5
         np.testing.assert_allclose(g[i], num, rtol=1e-3, atol=1e-5 * max(1.0, abs(f0), np.abs(g).max()))
+    # fused kernel vs torch autograd: same loss, same gradient
+    assert model.use_fused_fit
+    model.use_fused_fit = False
+    f_ref, g_ref = model._loss_and_grad(theta, layout)
+    model.use_fused_fit = True
+    np.testing.assert_allclose(f0, f_ref, rtol=1e-11)
+    np.testing.assert_allclose(g, g_ref, rtol=1e-7, atol=1e-9 * max(1.0, np.abs(g_ref).max()))
+    for trial in range(3):  # away from the defaults too, incl. the exponential prior on the noise
+        th = theta + np.random.default_rng(trial).normal(0, 0.4, size=theta.shape)
+        model.set_prior_on_observation_noise = trial == 2
+        fa, ga = model._loss_and_grad_fused(th, layout)
+        fb, gb = model._loss_and_grad_autograd(th, layout)
+        np.testing.assert_allclose(fa, fb, rtol=1e-10)
+        np.testing.assert_allclose(ga, gb, rtol=1e-6, atol=1e-9 * max(1.0, np.abs(gb).max()))
+    model.set_prior_on_observation_noise = False
     # the fit lowers the loss and keeps the parameters in their domains
     model.optimize_hps = True
     np.random.seed(0)

@@ -307,3 +307,30 @@ def test_large_and_odd_evaluated_sets(n_eval):
     np.testing.assert_allclose(mu.cpu().numpy()[idx], ref["mu"], rtol=1e-6, atol=1e-12)
     np.testing.assert_allclose(sigma.cpu().numpy()[idx], ref["sigma"], rtol=1e-6, atol=1e-12)
     np.testing.assert_allclose(ei.cpu().numpy()[idx], ref["acq"], rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("gen,d", [("CKSWithRQSearchSpace", 6), ("CompositionalKernelSearchSpace", 8), ("CKSHighDimSearchSpace", 12)])
+def test_large_grammars(gen, d):
+    """More base kernels / dim-wise columns than the benchmark grammars (B up to 24, F up to 36)."""
+    gram = Grammar.get(gen, d)
+    rng = np.random.default_rng(3)
+    ev = [rn.random_stress_tree(rng, gram.symbols, max_depth=4) for _ in range(40)]
+    ca = [rn.random_stress_tree(rng, gram.symbols, max_depth=5) for _ in range(150)]
+    ca[3] = ev[7]
+    XE, XC = sot.as_device_trees(encode(ev, gram), DEV), sot.as_device_trees(encode(ca, gram), DEV)
+    dense = sot.dense_feature_matrices(sot.featurize(XE, gram), sot.featurize(XC, gram))
+    for ours, ref in FEATS:
+        FE, FC = rn.dense_features(ev, ca, ref, gen, d)
+        assert np.array_equal(dense[ours][0], FE) and np.array_equal(dense[ours][1], FC), ref
+    hyp = rn.Hyper(**rn.H1)
+    w = hyp.alphas / hyp.alphas.sum()
+    y = rng.standard_normal(len(ev))
+    eng = sot.AcquisitionEngine(XE, torch.from_numpy(y), gram, w, hyp.variance, hyp.lengthscale, hyp.noise_variance, hyp.mean_c)
+    o = sot.sot_pairs(XC, eng.state, w, hyp.variance, hyp.lengthscale, want=("K", "Df"))
+    np.testing.assert_allclose(o["Df"].cpu().numpy(), rn.per_feature_distances(ca, ev, gen, d), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(o["K"].cpu().numpy(), rn.K(ca, ev, hyp, gen, d), rtol=1e-12)
+    ref = rn.acquisition_function(ev, y, ca, hyp, gen, d)
+    mu, sigma, ei = eng.acquire_device(XC)
+    np.testing.assert_allclose(mu.cpu().numpy(), ref["mu"], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(sigma.cpu().numpy(), ref["sigma"], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(ei.cpu().numpy(), ref["acq"], rtol=1e-6, atol=1e-12)
