@@ -334,3 +334,40 @@ def test_large_grammars(gen, d):
     np.testing.assert_allclose(mu.cpu().numpy(), ref["mu"], rtol=1e-6, atol=1e-12)
     np.testing.assert_allclose(sigma.cpu().numpy(), ref["sigma"], rtol=1e-6, atol=1e-12)
     np.testing.assert_allclose(ei.cpu().numpy(), ref["acq"], rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_randomised_configurations(seed):
+    """Differential fuzz: random search space, dimension, tree depth, set sizes and hyper-parameters."""
+    rng = np.random.default_rng(1000 + seed)
+    gen = ["CKSWithRQSearchSpace", "CKSHighDimSearchSpace", "CompositionalKernelSearchSpace", "NDimFullKernelsSearchSpace"][seed % 4]
+    d = int(rng.integers(1, 7))
+    gram = Grammar.get(gen, d)
+    n_eval, n_cand = int(rng.integers(1, 140)), int(rng.integers(1, 260))
+    depth_e, depth_c = int(rng.integers(0, 6)), int(rng.integers(0, 6))
+    p_leaf = float(rng.uniform(0.05, 0.6))
+    ev = [rn.random_stress_tree(rng, gram.symbols, max_depth=depth_e, p_leaf=p_leaf) for _ in range(n_eval)]
+    ca = [rn.random_stress_tree(rng, gram.symbols, max_depth=depth_c, p_leaf=p_leaf) for _ in range(n_cand)]
+    for k in range(0, n_cand, 17):  # sprinkle exact copies and child-swapped copies of evaluated trees
+        t = ev[int(rng.integers(n_eval))]
+        ca[k] = t if k % 2 else (t if isinstance(t, str) else (t[0], t[2], t[1]))
+    hyp = rn.Hyper(alphas=rng.uniform(0.05, 0.95, 3), lengthscale=float(rng.uniform(0.3, 3.0)), variance=float(rng.uniform(0.2, 3.0)),
+                   noise_variance=float(10 ** rng.uniform(-5, -2)), mean_c=float(rng.normal()))
+    w = hyp.alphas / hyp.alphas.sum()
+    y = rng.standard_normal(n_eval)
+    XE, XC = sot.as_device_trees(encode(ev, gram), DEV), sot.as_device_trees(encode(ca, gram), DEV)
+    dense = sot.dense_feature_matrices(sot.featurize(XE, gram), sot.featurize(XC, gram))
+    for ours, ref in FEATS:
+        FE, FC = rn.dense_features(ev, ca, ref, gen, d)
+        assert np.array_equal(dense[ours][0], FE) and np.array_equal(dense[ours][1], FC), (ref, gen, d)
+    eng = sot.AcquisitionEngine(XE, torch.from_numpy(y), gram, w, hyp.variance, hyp.lengthscale, hyp.noise_variance, hyp.mean_c)
+    o = sot.sot_pairs(XC, eng.state, w, hyp.variance, hyp.lengthscale, want=("K", "D", "Df"))
+    np.testing.assert_allclose(o["Df"].cpu().numpy(), rn.per_feature_distances(ca, ev, gen, d), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(o["K"].cpu().numpy(), rn.K(ca, ev, hyp, gen, d), rtol=1e-12)
+    ref = rn.acquisition_function(ev, y, ca, hyp, gen, d)
+    mu, sigma, ei = eng.acquire_device(XC)
+    ok = np.isfinite(ref["sigma"])  # sqrt of a slightly negative variance is NaN on both sides
+    assert np.array_equal(ok, np.isfinite(sigma.cpu().numpy())) or np.abs(ref["sigma"][~ok]).size < 3
+    np.testing.assert_allclose(mu.cpu().numpy(), ref["mu"], rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(sigma.cpu().numpy()[ok], ref["sigma"][ok], rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(ei.cpu().numpy()[ok], ref["acq"][ok], rtol=1e-6, atol=1e-10)
