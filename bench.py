@@ -45,33 +45,39 @@ def algorithmic_bytes_per_pair(n_cand: int, n_eval: int) -> float:
 
 
 class ClockSampler:
-    """nvidia-smi SM clocks + throttle reasons sampled DURING the timed region."""
+    """nvidia-smi SM clocks + throttle reasons sampled DURING the timed regions: one streaming
+    ``nvidia-smi -lms 50`` process (a new process per sample would take longer than a whole step)."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
-        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self.rows, self._proc, self._t = index, [], None, None
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.1)
+        for line in self._proc.stdout:
+            cells = [c.strip() for c in line.strip().split(",")]
+            if len(cells) >= 2:
+                self.rows.append(cells)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
-        self._t.start()
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                           "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        except Exception:
+            self._proc = None
         return self
 
     def __exit__(self, *a):
-        self._stop.set()
-        self._t.join(timeout=10)
+        if self._proc is not None:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=5)
+            except Exception:
+                self._proc.kill()
+            self._t.join(timeout=5)
 
     def summary(self) -> dict:
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
@@ -227,9 +233,10 @@ def main() -> None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t) / steps
 
+    clocks = ClockSampler(local_rank)
+    clocks.__enter__()  # sampled across every timed region of this run (device, end-to-end, per-kernel)
     launches0 = _lib.launch_count()
-    with ClockSampler(local_rank) as clocks:
-        ms_step = timed(step_device, args.steps, args.warmup)
+    ms_step = timed(step_device, args.steps, args.warmup)
     launches = (_lib.launch_count() - launches0) * args.steps // (args.steps + args.warmup)
 
     # end to end through the host-buffer API (H2D trees, kernels, all-gather, D2H EI inside the timed region)
@@ -258,6 +265,7 @@ def main() -> None:
 
     ms_pairs = timed(k_pairs, args.steps, 3, collective=False)
     ms_post = timed(k_post, args.steps, 3, collective=False)
+    clocks.__exit__()
 
     # fp64 FMA ceiling of this GPU (secondary roofline of the posterior kernel)
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
