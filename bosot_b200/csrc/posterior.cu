@@ -499,6 +499,36 @@ __global__ void fp64_mma_pattern_kernel(double* out, int iters) {
   if (sacc == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = sacc;
 }
 
+// even warps: DMMA chains, odd warps: DFMA chains -- do the two share the fp64 execution units?
+__global__ void fp64_mixed_probe_kernel(double* out, int iters) {
+  const bool tensor = ((threadIdx.x >> 5) & 1) == 0;
+  double d[8][2];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { d[k][0] = 1.0 + 1e-9 * k; d[k][1] = 0.5; }
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x, c = 1e-13;
+  if (tensor) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dmma8x8x4(d[k][0], d[k][1], a, b);
+    }
+  } else {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { d[k][0] = fma(d[k][0], b, c); d[k][1] = fma(d[k][1], b, c); }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { d[k][0] = fma(d[k][0], b, c); d[k][1] = fma(d[k][1], b, c); }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { d[k][0] = fma(d[k][0], b, c); d[k][1] = fma(d[k][1], b, c); }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { d[k][0] = fma(d[k][0], b, c); d[k][1] = fma(d[k][1], b, c); }
+    }
+  }
+  double sacc = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sacc += d[k][0] + d[k][1];
+  if (sacc == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = sacc;
+}
+
 int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval, const double* d_Linv, int ldl,
                      const double* d_beta, double mean_c, double variance, int acq_kind, const double* d_current_max,
                      double xi, double ucb_beta, double* d_mu, double* d_sigma, double* d_acq, cudaStream_t stream) {
@@ -611,6 +641,7 @@ extern "C" int bosot_fp64_mma_probe2(double* d_out, int n_blocks, int n_threads,
     case 7: fp64_mma_pattern_kernel<8, 1, false><<<n_blocks, n_threads, 0, st>>>(d_out, it); break;
     case 8: fp64_mma_pattern_kernel<1, 16, true><<<n_blocks, n_threads, 0, st>>>(d_out, it); break;
     case 9: fp64_mma_pattern_kernel<16, 1, false><<<n_blocks, n_threads, 0, st>>>(d_out, it); break;
+    case 15: fp64_mixed_probe_kernel<<<n_blocks, n_threads, 0, st>>>(d_out, it); break;
     default: return set_error(BOSOT_EINVAL, "bosot_fp64_mma_probe2: unknown pattern");
   }
   return after_launch("fp64_mma_pattern_kernel");

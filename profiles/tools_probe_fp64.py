@@ -31,3 +31,16 @@ for pat, (na, nbf, order) in pats.items():
         a.record(); lib.bosot_fp64_mma_probe2(out.data_ptr(), nb, threads, arg, st); b.record(); torch.cuda.synchronize()
         fl = 2.0*nb*(threads//32)*na*nbf*256*2048
         print("NA=%d NB=%d %s warps/SM %d: %.2f TF" % (na, nbf, order, threads//32, fl/(a.elapsed_time(b)*1e-3)/1e12))
+
+print("--- mixed: even warps DMMA (8 per iteration), odd warps DFMA (64 per iteration per lane)")
+for threads in (256, 512, 1024):
+    nb = sms
+    arg = (2048 << 4) | 15
+    for _ in range(2): lib.bosot_fp64_mma_probe2(out.data_ptr(), nb, threads, arg, st)
+    a=torch.cuda.Event(enable_timing=True); b=torch.cuda.Event(enable_timing=True)
+    a.record(); lib.bosot_fp64_mma_probe2(out.data_ptr(), nb, threads, arg, st); b.record(); torch.cuda.synchronize()
+    w = threads // 32
+    fl_t = 2.0*nb*(w//2)*8*256*2048
+    fl_f = 2.0*nb*(w//2)*32*64*2048
+    ms = a.elapsed_time(b)
+    print("warps/SM %d: DMMA part %.2f TF + DFMA part %.2f TF = %.2f TF" % (w, fl_t/(ms*1e-3)/1e12, fl_f/(ms*1e-3)/1e12, (fl_t+fl_f)/(ms*1e-3)/1e12))
