@@ -168,16 +168,27 @@ extern "C" int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const 
   int32_t* d_status = reinterpret_cast<int32_t*>(w + W.off_status);
   uint8_t* d_recs = w + W.off_recs;
 
+  int n_chunks = (int)(n_cand / 200000);
+  if (n_chunks > kMaxChunks) n_chunks = kMaxChunks;
+  if (n_chunks <= 1) {
+    // small pool: nothing to overlap, keep everything on the caller's stream (no cross-stream event hops)
+    if (int rc = cuda_check(cudaMemcpyAsync(d_trees, h_trees, (size_t)n_cand * kTreeBytes, cudaMemcpyHostToDevice, st), "H2D trees")) return rc;
+    if (int rc = launch_pairs(d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale, d_K, nullptr, nullptr, W.ld,
+                              d_status, d_recs, pairs_scratch_bytes(n_cand), st)) return rc;
+    if (int rc = launch_posterior(d_K, n_cand, W.ld, n_eval, d_Linv, ldl, d_beta, mean_c, variance, acq_kind, d_current_max, xi, ucb_beta,
+                                  h_mu ? d_mu : nullptr, h_sigma ? d_sigma : nullptr, h_acq ? d_acq : nullptr, st)) return rc;
+    const size_t nb = sizeof(double) * (size_t)n_cand;
+    if (h_mu) if (int rc = cuda_check(cudaMemcpyAsync(h_mu, d_mu, nb, cudaMemcpyDeviceToHost, st), "D2H mu")) return rc;
+    if (h_sigma) if (int rc = cuda_check(cudaMemcpyAsync(h_sigma, d_sigma, nb, cudaMemcpyDeviceToHost, st), "D2H sigma")) return rc;
+    if (h_acq) if (int rc = cuda_check(cudaMemcpyAsync(h_acq, d_acq, nb, cudaMemcpyDeviceToHost, st), "D2H acq")) return rc;
+    return BOSOT_OK;
+  }
+  const int64_t per = ((n_cand + n_chunks - 1) / n_chunks + 63) & ~(int64_t)63;  // whole posterior tiles per chunk
   int dev = 0;
   if (int rc = cuda_check(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
   std::lock_guard<std::mutex> lock(g_pipe_mutex);
   HostPipe* P = nullptr;
   if (int rc = host_pipe(dev, &P)) return rc;
-
-  int n_chunks = (int)(n_cand / 200000);
-  if (n_chunks < 1) n_chunks = 1;
-  if (n_chunks > kMaxChunks) n_chunks = kMaxChunks;
-  const int64_t per = ((n_cand + n_chunks - 1) / n_chunks + 63) & ~(int64_t)63;  // whole posterior tiles per chunk
 
   // fork: both copy streams start after everything already queued on the caller's stream
   if (int rc = cuda_check(cudaEventRecord(P->start, st), "cudaEventRecord")) return rc;

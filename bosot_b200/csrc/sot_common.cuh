@@ -64,10 +64,14 @@ __device__ __forceinline__ uint32_t path_child_code(uint32_t cur, uint32_t o) {
   return 1 + 2 * len + o;
 }
 
-// One thread scans one tree record (already copied to rec + kRecTok).
-// Backward pass over the pre-order tokens = stack evaluation -> class id of every operator
-// node; forward pass = top-down propagation of the reduced-path state -> (symbol, code) of
-// every leaf.  Writes meta bytes; returns 0 or a BOSOT_TREE_* defect code.
+// One thread scans one tree record (already copied to rec + kRecTok).  Three passes, arranged so that the
+// threads of a warp (32 different trees) diverge as little as possible:
+//   1. backward over the pre-order tokens = stack evaluation of the STRUCTURE only: for every operator node
+//      (numbered in reverse pre-order) the references of its two children -- a few instructions per token;
+//   2. over the operator nodes in that order (children always come first): the 64-bit class id -- the
+//      expensive mixing runs in lock step, every lane busy until its own tree runs out of operators;
+//   3. forward = top-down propagation of the reduced-path state -> (symbol, code) of every leaf.
+// Writes the meta bytes; returns 0 or a BOSOT_TREE_* defect code.
 __device__ __forceinline__ int scan_tree(uint8_t* rec, int n_symbols) {
   uint64_t* iid = reinterpret_cast<uint64_t*>(rec + kRecIid);
   const uint8_t* tok = rec + kRecTok + 1;
@@ -92,15 +96,20 @@ __device__ __forceinline__ int scan_tree(uint8_t* rec, int n_symbols) {
         if (sp < 2 || n_int >= kMaxInternal) { status = BOSOT_TREE_BAD_SHAPE; break; }
         const uint32_t a = st[sp - 1], b = st[sp - 2];
         sp -= 2;
-        const uint64_t ia = (a & 0x80) ? iid[a & 0x7f] : leaf_class(a);
-        const uint64_t ib = (b & 0x80) ? iid[b & 0x7f] : leaf_class(b);
-        iid[n_int] = class_combine(t - 0x7f, ia, ib);
+        iid[n_int] = (uint64_t)(a | (b << 8) | ((t - 0x7f) << 16));  // children + operator, replaced by the id in pass 2
         st[sp++] = (uint8_t)(0x80 | n_int);
         ++n_int;
       }
     }
     if (status == 0 && sp != 1) status = BOSOT_TREE_BAD_SHAPE;
     if (status == 0) {
+      for (int r = 0; r < n_int; ++r) {
+        const uint32_t packed = (uint32_t)iid[r];
+        const uint32_t a = packed & 0xff, b = (packed >> 8) & 0xff, op = packed >> 16;
+        const uint64_t ia = (a & 0x80) ? iid[a & 0x7f] : leaf_class(a);
+        const uint64_t ib = (b & 0x80) ? iid[b & 0x7f] : leaf_class(b);
+        iid[r] = class_combine(op, ia, ib);
+      }
       sp = 0;
       uint32_t cur = 0;
       for (int i = 0; i < n; ++i) {
