@@ -37,29 +37,25 @@ class BayesianOptimizerObjects:
         do_plotting: bool = False,
         **kwargs
     ):
+        # acquisition set-up
         self.acquisition_function_type = acquisition_function_type
-        self.validation_type = validation_type
-        self.do_plotting = do_plotting
         self.acquisiton_optimization_type = acquisiton_optimization_type
-        self.current_bests = []
-        self.query_list = []
-        self.additional_metrics = []
-        self.iteration_time_list = []
-        self.acquisition_time_list = []
-        self.oracle_time_list = []
-        self.query_durations_x_data = []
-        self.additional_metrics_index_interval = 10
-        self.n_prune_trailing = n_prune_trailing
+        self.gp_ucb_beta, self.ei_xi = 3.0, 0.01
         self.population_evolutionary = population_evolutionary
         self.n_steps_evolutionary = n_steps_evolutionary
         self.num_offspring_evolutionary = num_offspring_evolutionary
-        self.validation_metrics = []
-        self.oracle = None
-        self.gp_ucb_beta = 3.0
-        self.ei_xi = 0.01
+        self.n_prune_trailing = n_prune_trailing
         # EA on flat records (GPU population, same np.random consumption => same proposals as the object EA);
         # switched off automatically when the set-up is not the plain kernel-grammar one
         self.use_flat_evolutionary = True
+        # bookkeeping of a run (same attribute names as the reference, they are read by its scripts)
+        self.validation_type = validation_type
+        self.do_plotting = do_plotting
+        self.additional_metrics_index_interval = 10
+        for trace in ("current_bests", "query_list", "additional_metrics", "validation_metrics", "iteration_time_list",
+                      "acquisition_time_list", "oracle_time_list", "query_durations_x_data"):
+            setattr(self, trace, [])
+        self.oracle = None
 
     # ---- wiring -----------------------------------------------------------------------------
     def set_oracle(self, oracle):

@@ -1,23 +1,22 @@
-"""bosot/bayesian_optimization/enums.py:20-38."""
+"""Enumerations of the BO layer.  Member names and values are the reference's
+(bosot/bayesian_optimization/enums.py:20-38) because configs and scripts refer to them by name."""
 from enum import Enum
 
-
-class AcquisitionFunctionType(Enum):
-    GP_UCB = 1
-    EXPECTED_IMPROVEMENT = 2
-    RANDOM = 3
-    EXPECTED_IMPROVEMENT_PER_SECOND = 4
-
-
-class ValidationType(Enum):
-    MAX_OBSERVED = 1
-
-    @staticmethod
-    def get_name(val_type):
-        if val_type == ValidationType.MAX_OBSERVED:
-            return "MAXOBSERVED"
+_MEMBERS = {
+    "AcquisitionFunctionType": ("GP_UCB", "EXPECTED_IMPROVEMENT", "RANDOM", "EXPECTED_IMPROVEMENT_PER_SECOND"),
+    "ValidationType": ("MAX_OBSERVED",),
+    "AcquisitionOptimizationObjectBOType": ("TRAILING_CANDIDATES", "EVOLUTIONARY"),
+}
 
 
-class AcquisitionOptimizationObjectBOType(Enum):
-    TRAILING_CANDIDATES = 1
-    EVOLUTIONARY = 2
+def _make(name):
+    # values count from 1 in declaration order, as in the reference
+    return Enum(name, {member: i + 1 for i, member in enumerate(_MEMBERS[name])}, module=__name__)
+
+
+AcquisitionFunctionType = _make("AcquisitionFunctionType")
+AcquisitionOptimizationObjectBOType = _make("AcquisitionOptimizationObjectBOType")
+ValidationType = _make("ValidationType")
+
+_VALIDATION_LABELS = {ValidationType.MAX_OBSERVED: "MAXOBSERVED"}
+ValidationType.get_name = staticmethod(lambda val_type: _VALIDATION_LABELS.get(val_type))
