@@ -40,6 +40,26 @@ class BosotGrammar(C.Structure):
     ]
 
 
+class BosotHellingerSpace(C.Structure):
+    """Mirror of ``struct bosot_hellinger_space``."""
+
+    _fields_ = [
+        ("n_symbols", C.c_int32),
+        ("input_dimension", C.c_int32),
+        ("n_virtual", C.c_int32),
+        ("n_samples", C.c_int32),
+        ("n_sobol_dims", C.c_int32),
+        ("n_priors", C.c_int32),
+        ("sym_kind", C.c_uint8 * MAX_SYMBOLS),
+        ("sym_dim", C.c_int8 * MAX_SYMBOLS),
+        ("prior_of", (C.c_uint8 * 3) * 4),
+    ]
+
+
+HK_RBF, HK_LINEAR, HK_PERIODIC, HK_RQ = 0, 1, 2, 3
+HELLINGER_MAX_VIRTUAL = 20
+HELLINGER_MAX_DIM = 16
+
 # every symbol include/bosot_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _D3 = C.POINTER(C.c_double)
@@ -72,6 +92,9 @@ SIGNATURES = {
     "bosot_neighbours": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P, _P]),
     "bosot_gp_fit_max_eval": (C.c_int, []),
     "bosot_gp_nll_grad": (C.c_int, [_P, C.c_int, C.c_int64, _P, _D3, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P]),
+    "bosot_hellinger_record_doubles": (C.c_int, [C.c_int]),
+    "bosot_hellinger_grams": (C.c_int, [_P, C.c_int64, C.POINTER(BosotHellingerSpace), _P, _P, _P, _P, _P, _P]),
+    "bosot_hellinger_pairs": (C.c_int, [_P, _P, C.c_int64, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double, _P, _P, C.c_int64, _P, _P]),
     "bosot_fp64_fma_probe": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "bosot_fp64_mma_probe": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "bosot_fp64_mma_probe2": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),

@@ -105,6 +105,7 @@ int bosot_abi_version(void);
 #define BOSOT_TREE_BAD_SHAPE 3
 #define BOSOT_NEIGHBOUR_BAD_INDEX 4
 #define BOSOT_NEIGHBOUR_TOO_BIG 5 /* the move would exceed 63 nodes */
+#define BOSOT_HELLINGER_TOO_MANY_PARAMS 6 /* more hyper-parameters than columns of the quantile table */
 
 int bosot_featurize(const uint8_t* d_trees, int64_t n_trees, const bosot_grammar* grammar,
                     uint8_t* d_n_nodes, uint8_t* d_n_leaves,
@@ -214,6 +215,57 @@ int bosot_gp_nll_grad(const double* d_Df, int n_eval, int64_t ld, const double* 
  * BOSOT_TREE_* / BOSOT_NEIGHBOUR_* code; on error the input tree is copied through unchanged. */
 int bosot_neighbours(const uint8_t* d_trees, int64_t n_trees, const int64_t* d_index, int n_symbols,
                      uint8_t* d_out, int32_t* d_status, void* stream);
+
+/* ---- Hellinger kernel-kernel --------------------------------------------------
+ * The alternative kernel-kernel behind the same BaseObjectKernel API (reference
+ * kernels/kernel_kernel_hellinger.py:104-259): every tree is turned into S Gram matrices of its composed
+ * kernel on V virtual points, one per hyper-parameter sample (sample_over_hps, :192-212); the distance of two
+ * trees is the mean over samples of 1 - exp(logdet(K1)/4 + logdet(K2)/4 - logdet((K1+K2)/2 + jitter)/2)
+ * (hellinger_distance / expected_hellinger_distance, :160-190), samples whose term is NaN or negative
+ * are left out; K = variance * exp(-0.5 * d / lengthscale^2) (:128-132).  jitter = 1e-6 (:126).
+ *
+ * bosot_hellinger_space: what the reference reads from the leaf kernels.  Symbols are those of bosot_grammar.
+ * Parameters of a tree are numbered leaf by leaf, left to right, inside a leaf in GPflow's
+ * trainable_parameters order: RBF (lengthscales[nd], variance), LINEAR (offset, variance),
+ * PERIODIC (period, lengthscales[nd], variance), RQ (alpha, lengthscales[nd], variance); nd = 1 for a kernel on
+ * one dimension, input_dimension otherwise.  Parameter number j of sample i takes the value
+ * d_quantiles[(prior * n_samples + i) * n_sobol_dims + j] = quantile of its prior at Sobol coordinate (i, j)
+ * (tfd.Gamma(a, b).quantile(tf.math.sobol_sample(n_params, S)[i, j]), :199-207); the table is built by the host.
+ */
+#define BOSOT_HELLINGER_MAX_VIRTUAL 20
+#define BOSOT_HELLINGER_MAX_DIM 16
+#define BOSOT_HK_RBF 0
+#define BOSOT_HK_LINEAR 1
+#define BOSOT_HK_PERIODIC 2
+#define BOSOT_HK_RQ 3
+typedef struct bosot_hellinger_space {
+  int32_t n_symbols;
+  int32_t input_dimension;               /* <= BOSOT_HELLINGER_MAX_DIM */
+  int32_t n_virtual;                     /* V <= BOSOT_HELLINGER_MAX_VIRTUAL */
+  int32_t n_samples;                     /* S = num_param_samples */
+  int32_t n_sobol_dims;                  /* columns of the quantile table; >= parameters of any tree passed */
+  int32_t n_priors;                      /* planes of the quantile table */
+  uint8_t sym_kind[BOSOT_MAX_SYMBOLS];   /* BOSOT_HK_* */
+  int8_t sym_dim[BOSOT_MAX_SYMBOLS];     /* active dimension, -1 = all dimensions */
+  uint8_t prior_of[4][3];                /* quantile plane of (kind, parameter slot in the order above) */
+} bosot_hellinger_space;
+
+/* Doubles per (tree, sample) record of the Gram store for V virtual points (the lower triangle in the
+ * column-cyclic 4-lane order the pair kernel factorises in, jitter already on the diagonal). */
+int bosot_hellinger_record_doubles(int n_virtual);
+/* Gram store of n_trees trees: d_G [S][n_trees][record] and d_logdet [S][n_trees] = log|det(K + jitter I)|.
+ * d_virtual_X: [V][input_dimension] row-major.  d_status: int32[n_trees], 0 or a BOSOT_TREE_* code (then NaN Grams). */
+int bosot_hellinger_grams(const uint8_t* d_trees, int64_t n_trees, const bosot_hellinger_space* space,
+                          const double* d_virtual_X, const double* d_quantiles,
+                          double* d_G, double* d_logdet, int32_t* d_status, void* stream);
+/* K[a][b] (and / or D[a][b]), a < n_a rows, b < n_b columns, leading dimension ld >= n_b, from two Gram stores
+ * (the same store twice gives the symmetric K(X, X)).  d_info: int64[2] (zeroed by the call): [0] (pair, sample)
+ * terms left out as NaN / negative, [1] pairs without any valid sample (their D and K are NaN; the reference
+ * divides by zero there). */
+int bosot_hellinger_pairs(const double* d_Ga, const double* d_logdet_a, int64_t n_a,
+                          const double* d_Gb, const double* d_logdet_b, int64_t n_b,
+                          int n_virtual, int n_samples, double variance, double lengthscale,
+                          double* d_K, double* d_D, int64_t ld, int64_t* d_info, void* stream);
 
 /* ---- measurement helpers -----------------------------------------------------------------
  * bosot_fp64_fma_probe / bosot_fp64_mma_probe: run `iters` x 8 independent DFMA (resp. fp64
