@@ -1,23 +1,28 @@
 // Hellinger kernel-kernel: expected Hellinger distance between the GP priors of two
 // kernel-grammar trees (reference bosot/kernels/kernel_kernel_hellinger.py:104-259).
 //
-// Two launches:
-//   hellinger_gram_kernel<VP>  one CTA per tree: for every hyper-parameter sample the Gram of the composed
-//                              kernel on the V virtual points (sample_over_hps, :192-212) and its log|det|;
-//   hellinger_pair_kernel<VP>  one CTA per 32 x 16 tile of (row tree, column tree) pairs, looping over the
-//                              samples: log|det| of K1 + K2 for every (pair, sample) -> mean distance -> K.
+// Three kernels:
+//   hellinger_gram_kernel<VP>    one CTA per tree: for every hyper-parameter sample the Gram of the composed
+//                                kernel on the V virtual points (sample_over_hps, :192-212);
+//   hellinger_logdet_kernel<VP>  log|det| of every stored Gram (get_slog_det, :214-218);
+//   hellinger_pair_kernel<VP>    one CTA per 36 x 8 tile of (row tree, column tree) pairs, looping over the
+//                                samples: det(K1 + K2) for every (pair, sample) -> mean distance -> K.
 // The pair kernel is the hot one: S * n_a * n_b symmetric V x V determinants (V = 20: 1330 fused
-// multiply-adds each), fp64-pipe bound.  A matrix is factorised (LDL^T, no pivoting: the matrices are
-// Gram + jitter) by FOUR lanes that keep the lower triangle in registers, column j on lane j mod 4; the
-// pivot column travels by warp shuffle, so no shared-memory traffic besides reading the two operands once.
-// Operands are staged per sample by TMA bulk copies (double buffered) in exactly the order the lanes
-// consume them: element (slot m, row i, lane r) = K[i][4m + r] at ((base_m + i - 4m) * 4 + r), records
-// padded to a stride = 4 (mod 16) doubles so that the four groups of a half-warp hit distinct banks.
+// multiply-adds each).  A matrix is factorised (LDL^T, no pivoting: Gram + jitter) by FOUR lanes that keep
+// the lower triangle in registers, column j on lane j mod 4; per step the pivot column goes through a small
+// per-group shared-memory scratch (one 16-byte store per two rows by the owner, 16-byte broadcast loads by
+// all four lanes: half the shared-memory wavefronts of 64-bit warp shuffles, which bounded the first version).
+// Operands are staged per sample by TMA bulk copies (double buffered) in exactly the order the lanes consume
+// them: per-lane entry t = (slot m, row i) of lane r = K[i][4m + r] at ((t / 2) * 4 + r) * 2 + t % 2, records
+// padded to a stride = 8 (mod 16) doubles so that the groups of a quarter-warp hit distinct banks.  All eight
+// groups of a warp work on the same row tree: its record is read as a broadcast.
 //
 // logdet((K1 + K2) / 2 + jitter I) = logdet(K1' + K2') - V log 2 with K' = K + 2 jitter I: the store keeps
-// K' (what the reference caches is K + jitter I; its log|det| is computed here from K' - jitter I).
+// K' (what the reference caches is K + jitter I; its log|det| is computed from K' - jitter I).  The distance
+// 1 - exp(ld1 / 4 + ld2 / 4 - ld_avg / 2) is evaluated as 1 - det1^(1/4) det2^(1/4) / sqrt(det_avg).
 #include "sot_common.cuh"
 #include "launch.cuh"
+#include "fast_math.cuh"
 
 namespace bosot {
 
@@ -27,17 +32,26 @@ constexpr int kHMaxParamsSmem = 160 * 1024;
 template <int VP>
 struct HRec {
   static constexpr int kSlots = VP / 4;
-  static constexpr int kT = kSlots * VP - 2 * kSlots * (kSlots - 1);  // per-lane entries: sum_m (VP - 4m)
+  static constexpr int kT = kSlots * VP - 2 * kSlots * (kSlots - 1);  // per-lane entries: sum_m (VP - 4m), even
   static constexpr int kDoubles = 4 * kT;
-  static constexpr int kStride = ((kDoubles + 11) / 16) * 16 + 4;     // smallest value = 4 (mod 16) >= kDoubles
+  static constexpr int kStride = ((kDoubles + 7) / 16) * 16 + 8;      // smallest value = 8 (mod 16) >= kDoubles
   __host__ __device__ static constexpr int base(int m) { return m * VP - 2 * m * (m - 1); }
+  // per-lane entry t of lane r sits at pos(t, r): two consecutive entries of a lane form one 16-byte load
+  __host__ __device__ static constexpr int pos(int t, int r) { return ((t >> 1) * 4 + r) * 2 + (t & 1); }
 };
 
 __host__ __device__ inline int hellinger_vp(int v) { return (v + 3) & ~3; }
 
+__device__ __forceinline__ double2 lds128(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
 // ---- LDL^T of one symmetric matrix spread over 4 lanes; returns the product of the pivots in two halves ----
-// a[base(m) + i - 4m] = A[i][4m + r], i >= 4m.  Entries above the diagonal of a column and columns that are
-// already eliminated receive harmless updates (uniform trip counts: no divergence inside the warp).
+// a[base(m) + i - 4m] = A[i][4m + r], i >= 4m.  Step k: the lane owning column k hands it to the other three by
+// warp shuffles, four rows at a time in ascending order (l_j of a slot is known when its rows arrive, so only
+// four column entries are live at once), and every lane applies the rank-1 update to its own columns.  Entries
+// above the diagonal of a column and columns that are already eliminated receive harmless updates (uniform
+// trip counts: no divergence inside the warp).  Shared-memory bandwidth is the ceiling of this scheme: a
+// 64-bit shuffle costs two wavefronts, exactly what a 16-byte broadcast load per two rows would cost, without
+// the stores (measured: the shared-memory variant was 20 % slower).
 template <int VP>
 __device__ __forceinline__ void ldl_pivot_products(double (&a)[HRec<VP>::kT], int r, int lane0, double& p_lo, double& p_hi) {
   using R = HRec<VP>;
@@ -46,24 +60,31 @@ __device__ __forceinline__ void ldl_pivot_products(double (&a)[HRec<VP>::kT], in
 #pragma unroll
   for (int k = 0; k < VP; ++k) {
     const int q = k >> 2, rk = k & 3;
-    double c[VP];
-#pragma unroll
-    for (int i = k; i < VP; ++i) c[i] = __shfl_sync(0xffffffffu, a[R::base(q) + i - 4 * q], lane0 + rk);
-    const double d = c[k];
+    const double d = __shfl_sync(0xffffffffu, a[R::base(q) + k - 4 * q], lane0 + rk);
     if (k < VP / 2) p_lo *= d; else p_hi *= d;
     if (k + 1 < VP) {
-      const double inv = 1.0 / d;
+      const double inv = fast_rcp(d);
+      double lj[R::kSlots];
 #pragma unroll
-      for (int m = q; m < R::kSlots; ++m) {
-        // l_j = A[j][k] / d for this lane's column j = 4m + r (0 when the column is already eliminated)
-        double cj = 0.0;
+      for (int mb = q; mb < R::kSlots; ++mb) {
+        double c[4];
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr)
-          if (4 * m + rr > k && rr == r) cj = c[4 * m + rr];
-        const double lj = cj * inv;
+          if (4 * mb + rr > k) c[rr] = __shfl_sync(0xffffffffu, a[R::base(q) + 4 * mb + rr - 4 * q], lane0 + rk);
+        double cj = 0.0;  // A[j][k] for this lane's column j = 4 mb + r (0 when that column is already eliminated)
 #pragma unroll
-        for (int i = (4 * m > k + 1 ? 4 * m : k + 1); i < VP; ++i)
-          a[R::base(m) + i - 4 * m] = fma(-c[i], lj, a[R::base(m) + i - 4 * m]);
+        for (int rr = 0; rr < 4; ++rr)
+          if (4 * mb + rr > k && rr == r) cj = c[rr];
+        lj[mb] = cj * inv;
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const int i = 4 * mb + rr;
+          if (i > k) {
+#pragma unroll
+            for (int m = (rk == 3 ? q + 1 : q); m <= mb; ++m)
+              a[R::base(m) + i - 4 * m] = fma(-c[rr], lj[m], a[R::base(m) + i - 4 * m]);
+          }
+        }
       }
     }
   }
@@ -94,7 +115,7 @@ __device__ __forceinline__ double hellinger_leaf(const bosot_hellinger_space& sp
     case BOSOT_HK_RBF: {  // th = 1/lengthscales[nd], variance
       double r2 = 0.0;
       for (int a = 0; a < nd; ++a) { const double t = (xi[lo + a] - xj[lo + a]) * th[a]; r2 = fma(t, t, r2); }
-      return th[nd] * exp(-0.5 * r2);
+      return th[nd] * exp_nonpos(-0.5 * r2);
     }
     case BOSOT_HK_LINEAR: {  // th = offset, variance
       double s = 0.0;
@@ -107,12 +128,12 @@ __device__ __forceinline__ double hellinger_leaf(const bosot_hellinger_space& sp
         const double t = sin(3.14159265358979323846 * (xi[lo + a] - xj[lo + a]) * th[0]) * th[1 + a];
         r2 = fma(t, t, r2);
       }
-      return th[1 + nd] * exp(-0.5 * r2);
+      return th[1 + nd] * exp_nonpos(-0.5 * r2);
     }
     default: {  // RQ: th = alpha, 1/lengthscales[nd], variance
       double r2 = 0.0;
       for (int a = 0; a < nd; ++a) { const double t = (xi[lo + a] - xj[lo + a]) * th[1 + a]; r2 = fma(t, t, r2); }
-      return th[1 + nd] * pow(1.0 + 0.5 * r2 / th[0], -th[0]);
+      return th[1 + nd] * exp_nonpos(-th[0] * log_ge1(1.0 + 0.5 * r2 * fast_rcp(th[0])));  // (1 + r2 / (2 alpha))^-alpha
     }
   }
 }
@@ -176,17 +197,15 @@ __global__ void __launch_bounds__(256) hellinger_gram_kernel(GramParams p) {
   __syncthreads();
   const int defect = s_defect, n_par = s_nparams;
   const size_t rec_stride = R::kStride;
-  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-  if (defect) {
+  if (defect) {  // NaN records: every distance involving this tree drops all its samples
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     for (int s = warp; s < S; s += p.n_warps) {
       double* out = p.G + ((size_t)s * p.n_trees + tree) * rec_stride;
       for (int t = lane; t < R::kStride; t += 32) out[t] = qnan;
-      if (lane == 0) p.logdet[(size_t)s * p.n_trees + tree] = qnan;
     }
     return;
   }
   double* theta = sTheta + (size_t)warp * 8 * J;
-  const int g = lane >> 2, r = lane & 3;
   for (int s0 = warp * 8; s0 < S; s0 += p.n_warps * 8) {
     __syncwarp();
     for (int idx = lane; idx < 8 * n_par; idx += 32) {
@@ -197,65 +216,74 @@ __global__ void __launch_bounds__(256) hellinger_gram_kernel(GramParams p) {
       theta[gg * J + j] = (pl & 0x80) ? 1.0 / v : v;
     }
     __syncwarp();
-    // the 8 records of this warp: entry (slot m, row i, lane rr) = K[i][4m + rr] (+ 2 jitter on the diagonal)
-    for (int idx = lane; idx < 8 * R::kDoubles; idx += 32) {
-      const int gg = idx / R::kDoubles, pos = idx - gg * R::kDoubles;
+    // the 8 records of this warp: per-lane entry t of lane rr = K[i][4m + rr] (+ 2 jitter on the diagonal)
+    for (int idx = lane; idx < 8 * R::kStride; idx += 32) {
+      const int gg = idx / R::kStride, pos = idx - gg * R::kStride;
       const int s = s0 + gg;
       if (s >= S) break;
-      const int t = pos >> 2, rr = pos & 3;
-      const int i = sPosI[t], j = 4 * sPosM[t] + rr;
-      double val = 0.0;
-      if (i >= j) {
-        if (i >= V) {
-          val = i == j ? 1.0 : 0.0;  // padding up to a multiple of 4: identity block
-        } else {
-          double st[kMaxLeaves];
-          int sp = 0;
-          const double* th = theta + gg * J;
-          for (int q = n - 1; q >= 0; --q) {  // reversed pre-order = postfix with swapped operands
-            const uint32_t tk = sTok[q];
-            if (tk >= 0x80) {
-              const double lhs = st[sp - 1], rhs = st[sp - 2];
-              --sp;
-              st[sp - 1] = tk == BOSOT_OP_ADD ? lhs + rhs : lhs * rhs;
-            } else {
-              st[sp++] = hellinger_leaf(p.sp, tk, th + sOff[q], sX + i * d, sX + j * d);
+      double val = 0.0;  // also the tail padding of the record
+      if (pos < R::kDoubles) {
+        const int t = ((pos >> 3) << 1) | (pos & 1), rr = (pos >> 1) & 3;
+        const int i = sPosI[t], j = 4 * sPosM[t] + rr;
+        if (i >= j) {
+          if (i >= V) {
+            val = i == j ? 1.0 : 0.0;  // padding up to a multiple of 4: identity block
+          } else {
+            double st[kMaxLeaves];
+            int sp = 0;
+            const double* th = theta + gg * J;
+            for (int q = n - 1; q >= 0; --q) {  // reversed pre-order = postfix with swapped operands
+              const uint32_t tk = sTok[q];
+              if (tk >= 0x80) {
+                const double lhs = st[sp - 1], rhs = st[sp - 2];
+                --sp;
+                st[sp - 1] = tk == BOSOT_OP_ADD ? lhs + rhs : lhs * rhs;
+              } else {
+                st[sp++] = hellinger_leaf(p.sp, tk, th + sOff[q], sX + i * d, sX + j * d);
+              }
             }
+            val = st[0] + (i == j ? 2.0 * kHJitter : 0.0);
           }
-          val = st[0] + (i == j ? 2.0 * kHJitter : 0.0);
         }
       }
       p.G[((size_t)s * p.n_trees + tree) * rec_stride + pos] = val;
     }
-    __syncwarp();
-    // log|det(K + jitter I)|: group g of this warp factorises sample s0 + g
-    {
-      const int s = min(s0 + g, S - 1);
-      const double* in = p.G + ((size_t)s * p.n_trees + tree) * rec_stride;
-      double a[R::kT];
-#pragma unroll
-      for (int t = 0; t < R::kT; ++t) a[t] = in[4 * t + r];
-#pragma unroll
-      for (int m = 0; m < R::kSlots; ++m)
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr)
-          if (rr == r && 4 * m + rr < V) a[R::base(m) + rr] -= kHJitter;
-      double p_lo, p_hi;
-      ldl_pivot_products<VP>(a, r, lane & ~3, p_lo, p_hi);
-      if (r == 0 && s0 + g < S) p.logdet[(size_t)s * p.n_trees + tree] = log(fabs(p_lo)) + log(fabs(p_hi));
-    }
   }
-  for (int s = warp; s < S; s += p.n_warps) {  // tail of every record: finite padding for the bulk copies
-    double* out = p.G + ((size_t)s * p.n_trees + tree) * rec_stride;
-    for (int t = R::kDoubles + lane; t < R::kStride; t += 32) out[t] = 0.0;
+}
+
+// log|det(K + jitter I)| of every record of a store: one 4-lane group per (sample, tree)
+constexpr int kDetThreads = 256;
+template <int VP>
+__global__ void __launch_bounds__(kDetThreads) hellinger_logdet_kernel(const double* __restrict__ G, int64_t n_records, int V,
+                                                                       double* __restrict__ logdet) {
+  using R = HRec<VP>;
+  const int tid = threadIdx.x, r = tid & 3;
+  const int64_t rec = (int64_t)blockIdx.x * (kDetThreads / 4) + (tid >> 2);
+  const double* in = G + (size_t)min(rec, n_records - 1) * R::kStride;
+  double a[R::kT];
+#pragma unroll
+  for (int t = 0; t < R::kT; t += 2) {
+    const double2 v = *reinterpret_cast<const double2*>(in + R::pos(t, r));
+    a[t] = v.x;
+    a[t + 1] = v.y;
   }
+#pragma unroll
+  for (int m = 0; m < R::kSlots; ++m)
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr)
+      if (rr == r && 4 * m + rr < V) a[R::base(m) + rr] -= kHJitter;  // the store carries two jitters, the reference's Gram one
+  double p_lo, p_hi;
+  ldl_pivot_products<VP>(a, r, tid & 28, p_lo, p_hi);
+  if (r == 0 && rec < n_records) logdet[rec] = log(fabs(p_lo)) + log(fabs(p_hi));
 }
 
 // =====================================================================================================
 // pairs
 // =====================================================================================================
-constexpr int kPairThreads = 256;
-constexpr int kPairTA = 32, kPairTB = 16;
+constexpr int kPairThreads = 384;                   // 12 warps = 96 four-lane groups
+constexpr int kPairTB = 8;                          // the 8 groups of a warp: one row tree x 8 column trees
+constexpr int kPairPasses = 3;
+constexpr int kPairTA = (kPairThreads / 32) * kPairPasses;  // 36 row trees per tile
 
 struct PairParams {
   const double* Ga;
@@ -295,14 +323,27 @@ __device__ __forceinline__ void hl_mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 template <int VP>
+struct PairSmem {
+  using R = HRec<VP>;
+  static constexpr int kRecs = kPairTA + kPairTB;
+  static constexpr size_t kStageDoubles = (size_t)kRecs * R::kStride;
+  static constexpr size_t oRoot = 2 * kStageDoubles;                                  // doubles; [2][kRecs] det^(1/4)
+  static constexpr size_t oAcc = oRoot + 2 * kRecs;                                   // [TA*TB]
+  static constexpr size_t oCnt = oAcc + kPairTA * kPairTB;                            // int[TA*TB]
+  static constexpr size_t oBar = oCnt + (kPairTA * kPairTB + 1) / 2;                  // 2 mbarriers
+  static constexpr size_t kBytes = (oBar + 2) * sizeof(double);
+};
+
+template <int VP>
 __global__ void __launch_bounds__(kPairThreads, 1) hellinger_pair_kernel(PairParams p) {
   using R = HRec<VP>;
-  constexpr int kStageDoubles = (kPairTA + kPairTB) * R::kStride;
+  using L = PairSmem<VP>;
   extern __shared__ __align__(16) uint8_t smem[];
   double* stage0 = reinterpret_cast<double*>(smem);
-  double* sAcc = stage0 + 2 * kStageDoubles;                         // [512]
-  int* sCnt = reinterpret_cast<int*>(sAcc + kPairTA * kPairTB);     // [512]
-  uint64_t* full = reinterpret_cast<uint64_t*>(sCnt + kPairTA * kPairTB);
+  double* sRoot = stage0 + L::oRoot;
+  double* sAcc = stage0 + L::oAcc;
+  int* sCnt = reinterpret_cast<int*>(stage0 + L::oCnt);
+  uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + L::oBar);
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, r = lane & 3;
   const int64_t a0 = (int64_t)(blockIdx.x / p.tiles_b) * kPairTA;
@@ -316,37 +357,50 @@ __global__ void __launch_bounds__(kPairThreads, 1) hellinger_pair_kernel(PairPar
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < kPairTA * kPairTB; i += kPairThreads) { sAcc[i] = 0.0; sCnt[i] = 0; }
-  __syncthreads();
-  auto issue = [&](int s) {
-    double* dst = stage0 + (s & 1) * kStageDoubles;
+  auto issue = [&](int s) {  // operands of sample s: two TMA bulk copies into buffer s & 1
+    double* dst = stage0 + (s & 1) * L::kStageDoubles;
     hl_mbar_expect_tx(&full[s & 1], bytes_a + bytes_b);
     hl_bulk_g2s(dst, p.Ga + ((size_t)s * p.n_a + a0) * R::kStride, bytes_a, &full[s & 1]);
     hl_bulk_g2s(dst + kPairTA * R::kStride, p.Gb + ((size_t)s * p.n_b + b0) * R::kStride, bytes_b, &full[s & 1]);
   };
+  auto roots = [&](int s) {  // det(K + jitter I)^(1/4) of the tile's trees for sample s
+    if (tid < na) sRoot[(s & 1) * L::kRecs + tid] = exp(0.25 * p.lda[(size_t)s * p.n_a + a0 + tid]);
+    else if (tid >= kPairTA && tid < kPairTA + nb) sRoot[(s & 1) * L::kRecs + tid] = exp(0.25 * p.ldb[(size_t)s * p.n_b + b0 + tid - kPairTA]);
+  };
+  __syncthreads();
   if (tid == 0) issue(0);
+  roots(0);
+  __syncthreads();
 
+  const double scale = exp2(0.5 * VP);  // det((K1' + K2') / 2) = det(K1' + K2') / 2^VP
   for (int s = 0; s < p.S; ++s) {
-    if (tid == 0 && s + 1 < p.S) issue(s + 1);  // the other buffer was released by the barrier closing sample s - 1
+    if (s + 1 < p.S) {  // the other buffer was released by the barrier closing sample s - 1
+      if (tid == 0) issue(s + 1);
+      roots(s + 1);
+    }
     hl_mbar_wait(&full[s & 1], (s >> 1) & 1);
-    const double* sA = stage0 + (s & 1) * kStageDoubles;
+    const double* sA = stage0 + (s & 1) * L::kStageDoubles;
     const double* sB = sA + kPairTA * R::kStride;
+    const double* root = sRoot + (s & 1) * L::kRecs;
+    const int bi = g;
+    const double* Rb = sB + min(bi, nb - 1) * R::kStride;
 #pragma unroll 1
-    for (int u = 0; u < 8; ++u) {
-      // half-warp = 4 groups: the same row record (broadcast) and 4 consecutive column records (stride = 4 mod 16 banks)
-      const int bi = (g & 3) + 4 * (u & 3), ai = w + 8 * (g >> 2) + 16 * (u >> 2);
-      const bool valid = ai < na && bi < nb;
-      const double* Ra = sA + min(ai, na - 1) * R::kStride + r;
-      const double* Rb = sB + min(bi, nb - 1) * R::kStride + r;
+    for (int u = 0; u < kPairPasses; ++u) {
+      const int ai = w + (kPairThreads / 32) * u;  // the whole warp reads one row record (broadcast), 8 column records
+      const double* Ra = sA + min(ai, na - 1) * R::kStride;
       double a[R::kT];
 #pragma unroll
-      for (int t = 0; t < R::kT; ++t) a[t] = Ra[4 * t] + Rb[4 * t];
+      for (int t = 0; t < R::kT; t += 2) {
+        const double2 x = lds128(Ra + R::pos(t, r)), y = lds128(Rb + R::pos(t, r));
+        a[t] = x.x + y.x;
+        a[t + 1] = x.y + y.y;
+      }
       double p_lo, p_hi;
-      ldl_pivot_products<VP>(a, r, lane & ~3, p_lo, p_hi);
-      if (r == 0 && valid) {
-        const double ld_avg = log(fabs(p_lo)) + log(fabs(p_hi)) - VP * 0.69314718055994530942;
-        const double l1 = p.lda[(size_t)s * p.n_a + a0 + ai], l2 = p.ldb[(size_t)s * p.n_b + b0 + bi];
-        const double hd = 1.0 - exp(0.25 * l1 + 0.25 * l2 - 0.5 * ld_avg);  // hellinger_distance, :185-190
-        if (hd >= 0.0) {                                                     // false for NaN as well (:176-178)
+      ldl_pivot_products<VP>(a, r, lane & 28, p_lo, p_hi);
+      if (r == 0 && ai < na && bi < nb) {
+        // 1 - exp(logdet1 / 4 + logdet2 / 4 - logdet_avg / 2)  (hellinger_distance, :185-190) without the logarithms
+        const double hd = 1.0 - root[ai] * root[kPairTA + bi] * scale * rsqrt(fabs(p_lo * p_hi));
+        if (hd >= 0.0) {  // false for NaN as well (:176-178)
           const int slot = ai * kPairTB + bi;
           sAcc[slot] += hd;
           sCnt[slot] += 1;
@@ -377,7 +431,7 @@ int launch_grams(GramParams& p, cudaStream_t st) {
   using R = HRec<VP>;
   const int J = p.sp.n_sobol_dims, V = p.sp.n_virtual, d = p.sp.input_dimension;
   int n_warps = (p.sp.n_samples + 7) / 8;
-  if (n_warps > 8) n_warps = 8;  // 256 threads: the factorisation keeps 60 doubles per lane in registers
+  if (n_warps > 8) n_warps = 8;
   const size_t per_warp = (size_t)8 * J * sizeof(double);
   while (n_warps > 1 && n_warps * per_warp > (size_t)kHMaxParamsSmem) --n_warps;
   if (per_warp > (size_t)kHMaxParamsSmem) return set_error(BOSOT_EINVAL, "bosot_hellinger_grams: n_sobol_dims too large for shared memory");
@@ -386,13 +440,17 @@ int launch_grams(GramParams& p, cudaStream_t st) {
   if (int rc = cuda_check(cudaFuncSetAttribute(hellinger_gram_kernel<VP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
                           "cudaFuncSetAttribute(hellinger_gram_kernel)")) return rc;
   hellinger_gram_kernel<VP><<<(unsigned)p.n_trees, n_warps * 32, smem, st>>>(p);
-  return after_launch("hellinger_gram_kernel");
+  if (int rc = after_launch("hellinger_gram_kernel")) return rc;
+  const int64_t n_records = (int64_t)p.sp.n_samples * p.n_trees;
+  const int64_t blocks = (n_records + kDetThreads / 4 - 1) / (kDetThreads / 4);
+  if (blocks > 0x7fffffffLL) return set_error(BOSOT_EINVAL, "bosot_hellinger_grams: too many records for one launch");
+  hellinger_logdet_kernel<VP><<<(unsigned)blocks, kDetThreads, 0, st>>>(p.G, n_records, V, p.logdet);
+  return after_launch("hellinger_logdet_kernel");
 }
 
 template <int VP>
 int launch_pairs(PairParams& p, cudaStream_t st) {
-  using R = HRec<VP>;
-  const size_t smem = sizeof(double) * (2 * (size_t)(kPairTA + kPairTB) * R::kStride + kPairTA * kPairTB) + sizeof(int) * kPairTA * kPairTB + 16;
+  const size_t smem = PairSmem<VP>::kBytes;
   if (int rc = cuda_check(cudaFuncSetAttribute(hellinger_pair_kernel<VP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                           "cudaFuncSetAttribute(hellinger_pair_kernel)")) return rc;
   const int64_t tiles_a = (p.n_a + kPairTA - 1) / kPairTA;

@@ -250,8 +250,10 @@ typedef struct bosot_hellinger_space {
   uint8_t prior_of[4][3];                /* quantile plane of (kind, parameter slot in the order above) */
 } bosot_hellinger_space;
 
-/* Doubles per (tree, sample) record of the Gram store for V virtual points (the lower triangle in the
- * column-cyclic 4-lane order the pair kernel factorises in, jitter already on the diagonal). */
+/* Doubles per (tree, sample) record of the Gram store for V virtual points.  A record is opaque to callers:
+ * K + 2 jitter I, lower triangle, in the column-cyclic 4-lane order the pair kernel factorises in (V rounded up
+ * to a multiple of 4 with an identity block; entry (slot m, row i) of lane r = K[i][4m + r], two consecutive
+ * entries of a lane adjacent), padded so that consecutive records fall into different shared-memory banks. */
 int bosot_hellinger_record_doubles(int n_virtual);
 /* Gram store of n_trees trees: d_G [S][n_trees][record] and d_logdet [S][n_trees] = log|det(K + jitter I)|.
  * d_virtual_X: [V][input_dimension] row-major.  d_status: int32[n_trees], 0 or a BOSOT_TREE_* code (then NaN Grams). */

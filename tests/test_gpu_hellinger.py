@@ -18,7 +18,7 @@ DEV = "cuda:0"
 
 
 def _dense(record: np.ndarray, V: int) -> np.ndarray:
-    """One store record (column-cyclic 4-lane order) -> dense symmetric matrix."""
+    """One store record (column-cyclic 4-lane order, two consecutive entries of a lane adjacent) -> dense symmetric matrix."""
     VP = (V + 3) // 4 * 4
     M = np.zeros((VP, VP))
     t = 0
@@ -27,7 +27,7 @@ def _dense(record: np.ndarray, V: int) -> np.ndarray:
             for r in range(4):
                 j = 4 * m + r
                 if i >= j:
-                    M[i, j] = M[j, i] = record[4 * t + r]
+                    M[i, j] = M[j, i] = record[((t >> 1) * 4 + r) * 2 + (t & 1)]
             t += 1
     return M
 
@@ -116,4 +116,4 @@ def test_malformed_trees_and_bad_arguments():
     with pytest.raises(ValueError):
         hellinger.pairs(store, store, space, 1.0, 0.0)
     lib = _lib.load()
-    assert lib.bosot_hellinger_record_doubles(20) == 244 and lib.bosot_hellinger_record_doubles(21) < 0
+    assert lib.bosot_hellinger_record_doubles(20) == 248 and lib.bosot_hellinger_record_doubles(21) < 0
