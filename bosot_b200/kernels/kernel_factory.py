@@ -5,6 +5,7 @@ bosot/kernels/base_elementary_kernel.py:34-35) reaches the kernel-kernel; data-s
 belong to the oracle side, which is out of scope."""
 from ..configs.kernels.base_elementary_kernel_config import BaseElementaryKernelConfig
 from ..configs.kernels.grammar_tree_kernel_kernel_configs import OptimalTransportGrammarKernelConfig
+from ..configs.kernels.hellinger_kernel_kernel_configs import BasicHellingerKernelKernelConfig
 from .kernel_grammar.kernel_grammar import SymbolicKernel
 
 
@@ -20,4 +21,8 @@ class KernelFactory:
             from .kernel_kernel_grammar_tree import OptimalTransportKernelKernel
 
             return OptimalTransportKernelKernel(**kernel_config.dict())
+        if isinstance(kernel_config, BasicHellingerKernelKernelConfig):
+            from .kernel_kernel_hellinger import KernelKernelHellinger
+
+            return KernelKernelHellinger(**kernel_config.dict())
         raise NotImplementedError(type(kernel_config).__name__)

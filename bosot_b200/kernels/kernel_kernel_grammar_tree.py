@@ -122,6 +122,23 @@ class OptimalTransportKernelKernel(BaseKernelGrammarKernel):
             out[_DEVICE_ORDER.index(f)] += wf
         return out
 
+    # ---- what ObjectGpModel needs from a kernel-kernel ----------------------------------------
+    def gp_parameters(self):
+        """(name, Parameter) in GPflow's variable order."""
+        return [("alphas", self.alphas), ("lengthscale", self.lengthscale), ("variance", self.variance)]
+
+    hyperpriors = {}
+
+    def fit_planes(self, flat: FlatTrees):
+        """The three E x E per-feature distance matrices (constants of the hyper-parameter fit) + the evaluated-set state."""
+        state = sot.EvalState(flat.trees, flat.grammar)
+        return sot.sot_pairs(flat.trees, state, (1.0, 1.0, 1.0), 1.0, 1.0, want=("Df",))["Df"], state
+
+    def make_engine(self, model: dict, noise_variance: float, mean_c: float, acq_kind: int, xi: float, ucb_beta: float):
+        return sot.AcquisitionEngine(model["flat"].trees, model["y"], model["flat"].grammar, self.device_weights(), float(self.variance),
+                                     float(self.lengthscale), noise_variance, mean_c, acq_kind=acq_kind, xi=xi, ucb_beta=ucb_beta,
+                                     state=model["state"])
+
     def _pairs(self, X, X2, want: Sequence[str]):
         fx = self.flatten(X)
         fx2 = fx if X2 is None else self.flatten(X2)

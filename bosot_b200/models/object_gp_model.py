@@ -84,7 +84,7 @@ class ObjectGpModel:
 
     # ------------------------------------------------------------------ small helpers
     def _kernel_parameters(self) -> List[Parameter]:
-        return [self.kernel.alphas, self.kernel.lengthscale, self.kernel.variance]
+        return [p for _, p in self.kernel.gp_parameters()]
 
     def set_mean_function(self, mean_function: MeanFunction):
         self.use_mean_function = True
@@ -115,8 +115,7 @@ class ObjectGpModel:
         flat = self.kernel.flatten(x_data)
         y = np.asarray(y_data, dtype=np.float64).reshape(-1, 1)
         assert len(flat) == y.shape[0]
-        state = sot.EvalState(flat.trees, flat.grammar)
-        Df = sot.sot_pairs(flat.trees, state, (1.0, 1.0, 1.0), 1.0, 1.0, want=("Df",))["Df"]
+        Df, state = self.kernel.fit_planes(flat)
         self.likelihood_variance = Parameter(np.power(self.observation_noise, 2.0), trainable=self.train_likelihood_variance)
         self.model = dict(flat=flat, state=state, Df=Df, y=torch.from_numpy(y[:, 0].copy()).to(flat.trees.device))
         self._engine = None
@@ -136,13 +135,9 @@ class ObjectGpModel:
         sig_inv = lambda a: np.log(a) - np.log1p(-a)  # noqa: E731
         sig = lambda u: 1.0 / (1.0 + np.exp(-u))  # noqa: E731
         out = []
-        k = self.kernel
-        if k.alphas.trainable:
-            out.append((k.alphas, sig_inv, sig))
-        if k.lengthscale.trainable:
-            out.append((k.lengthscale, _softplus_inv, _softplus))
-        if k.variance.trainable:
-            out.append((k.variance, _softplus_inv, _softplus))
+        for name, p in self.kernel.gp_parameters():
+            if p.trainable:
+                out.append((p, sig_inv, sig) if name == "alphas" else (p, _softplus_inv, _softplus))
         if self.likelihood_variance.trainable:
             lo = LIKELIHOOD_VARIANCE_LOWER_BOUND
             out.append((self.likelihood_variance, lambda v: _softplus_inv(v - lo), lambda u: _softplus(u) + lo))
@@ -184,17 +179,22 @@ class ObjectGpModel:
             vals[name] = np.asarray(theta[pos : pos + n], dtype=np.float64)
             pos += n
         sig = lambda u: 1.0 / (1.0 + np.exp(-u))  # noqa: E731
-        alphas = sig(vals["alphas"]) if "alphas" in vals else np.asarray(k.alphas.numpy(), dtype=np.float64)
+        has_alphas = hasattr(k, "alphas")
+        if has_alphas:
+            alphas = sig(vals["alphas"]) if "alphas" in vals else np.asarray(k.alphas.numpy(), dtype=np.float64)
         ls = float(_softplus(vals["lengthscale"])[0]) if "lengthscale" in vals else float(k.lengthscale)
         var = float(_softplus(vals["variance"])[0]) if "variance" in vals else float(k.variance)
         lo = LIKELIHOOD_VARIANCE_LOWER_BOUND
         noise = float(_softplus(vals["noise"])[0]) + lo if "noise" in vals else float(self.likelihood_variance)
         c = float(vals["c"][0]) if "c" in vals else self.mean_function.value()
-        S = float(np.sum(alphas))
-        order = [_DEVICE_ORDER.index(f) for f in k.feature_type_list]
-        w3 = np.zeros(3)
-        for g, a in zip(order, alphas):
-            w3[g] += a / S
+        if has_alphas:
+            S = float(np.sum(alphas))
+            order = [_DEVICE_ORDER.index(f) for f in k.feature_type_list]
+            w3 = np.zeros(3)
+            for g, a in zip(order, alphas):
+                w3[g] += a / S
+        else:  # a kernel-kernel with a single distance plane (Hellinger)
+            w3 = np.asarray(k.device_weights(), dtype=np.float64)
         Df, y = self.model["Df"], self.model["y"]
         if getattr(self, "_fit_out", None) is None or self._fit_out.device != Df.device:
             self._fit_out = torch.empty(9, dtype=torch.float64, device=Df.device)
@@ -211,6 +211,14 @@ class ObjectGpModel:
             rate = 1.0 / np.power(self.expected_observation_noise, 2.0)
             loss -= np.log(rate) - rate * noise
             d_noise = d_noise + rate
+        for pname, (mu, sd) in getattr(k, "hyperpriors", {}).items():  # LogNormal log-density on the constrained value
+            x = ls if pname == "lengthscale" else var
+            loss -= -np.log(x * sd * np.sqrt(2.0 * np.pi)) - (np.log(x) - mu) ** 2 / (2.0 * sd * sd)
+            g = 1.0 / x + (np.log(x) - mu) / (sd * sd * x)
+            if pname == "lengthscale":
+                d_ls = d_ls + g
+            else:
+                d_var = d_var + g
         grads = []
         for name, n in layout:
             if name == "alphas":  # w_g = alpha_g / S, alpha = sigmoid(u)
@@ -236,7 +244,9 @@ class ObjectGpModel:
             pos += n
         k = self.kernel
         as_t = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float64), device=dev)  # noqa: E731
-        alphas = torch.sigmoid(vals["alphas"]) if "alphas" in vals else as_t(k.alphas.numpy())
+        has_alphas = hasattr(k, "alphas")
+        if has_alphas:
+            alphas = torch.sigmoid(vals["alphas"]) if "alphas" in vals else as_t(k.alphas.numpy())
         ls = torch.nn.functional.softplus(vals["lengthscale"])[0] if "lengthscale" in vals else as_t(k.lengthscale.numpy())
         var = torch.nn.functional.softplus(vals["variance"])[0] if "variance" in vals else as_t(k.variance.numpy())
         if "noise" in vals:
@@ -244,10 +254,13 @@ class ObjectGpModel:
         else:
             noise = as_t(self.likelihood_variance.numpy())
         c = vals["c"][0] if "c" in vals else as_t(self.mean_function.value())
-        w3 = torch.zeros(3, dtype=torch.float64, device=dev)
-        w = alphas / alphas.sum()
-        idx = torch.tensor([_DEVICE_ORDER.index(f) for f in k.feature_type_list], device=dev)
-        w3 = w3.index_add(0, idx, w)
+        if has_alphas:
+            w3 = torch.zeros(3, dtype=torch.float64, device=dev)
+            w = alphas / alphas.sum()
+            idx = torch.tensor([_DEVICE_ORDER.index(f) for f in k.feature_type_list], device=dev)
+            w3 = w3.index_add(0, idx, w)
+        else:
+            w3 = as_t(k.device_weights())
         D = (w3[:, None, None] * self.model["Df"]).sum(0)
         E = D.shape[0]
         Kmat = var * torch.exp(-D / (ls * ls)) + noise * torch.eye(E, dtype=torch.float64, device=dev)
@@ -259,6 +272,9 @@ class ObjectGpModel:
         if self.set_prior_on_observation_noise:  # tfd.Exponential(rate) log-density on the constrained value
             rate = 1.0 / np.power(self.expected_observation_noise, 2.0)
             loss = loss - (np.log(rate) - rate * noise)
+        for pname, (mu, sd) in getattr(k, "hyperpriors", {}).items():
+            x = ls if pname == "lengthscale" else var
+            loss = loss - (-torch.log(x * sd * np.sqrt(2.0 * np.pi)) - (torch.log(x) - mu) ** 2 / (2.0 * sd * sd))
         (g,) = torch.autograd.grad(loss, t, allow_unused=True)
         return float(loss.detach()), (g.cpu().numpy() if g is not None else np.zeros_like(theta))
 
@@ -267,8 +283,8 @@ class ObjectGpModel:
         return self._loss_and_grad(theta, layout)[0]
 
     def _pack(self):
-        names = {id(self.kernel.alphas): "alphas", id(self.kernel.lengthscale): "lengthscale", id(self.kernel.variance): "variance",
-                 id(self.likelihood_variance): "noise"}
+        names = {id(p): name for name, p in self.kernel.gp_parameters()}
+        names[id(self.likelihood_variance)] = "noise"
         layout, chunks, items = [], [], self._trainables()
         for p, to_u, _ in items:
             u = np.atleast_1d(to_u(p.numpy())).astype(np.float64)
@@ -332,17 +348,12 @@ class ObjectGpModel:
             self.set_prior_on_observation_noise = saved
 
     # -------------------------------------------------------------------------- prediction
-    def engine(self, acq_kind: int = _lib.ACQ_NONE, xi: float = 0.01, ucb_beta: float = 3.0) -> sot.AcquisitionEngine:
+    def engine(self, acq_kind: int = _lib.ACQ_NONE, xi: float = 0.01, ucb_beta: float = 3.0):
         """Evaluated-set state + Cholesky for the current hyper-parameters (cached until they change)."""
         key = (acq_kind, xi, ucb_beta, tuple(self.kernel.device_weights()), float(self.kernel.variance), float(self.kernel.lengthscale),
                float(self.likelihood_variance), self.mean_function.value())
         if self._engine is None or self._engine[0] != key:
-            m = self.model
-            eng = sot.AcquisitionEngine(
-                m["flat"].trees, m["y"], m["flat"].grammar, self.kernel.device_weights(), float(self.kernel.variance),
-                float(self.kernel.lengthscale), float(self.likelihood_variance), self.mean_function.value(),
-                acq_kind=acq_kind, xi=xi, ucb_beta=ucb_beta, state=m["state"],
-            )
+            eng = self.kernel.make_engine(self.model, float(self.likelihood_variance), self.mean_function.value(), acq_kind, xi, ucb_beta)
             self._engine = (key, eng)
         return self._engine[1]
 
