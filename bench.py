@@ -302,6 +302,39 @@ def main() -> None:
                   ei_candidates_per_s=C4_POOL / (ms4 * 1e-3), e2e_ms=ms4_e2e, e2e_pairs_per_s=C4_POOL * C4_EVAL / (ms4_e2e * 1e-3),
                   e2e_ei_candidates_per_s=C4_POOL / (ms4_e2e * 1e-3))
 
+    # Hellinger kernel-kernel at the same 10k x 50 shape: S = 100 hyper-parameter samples, V = 20 virtual points
+    hell = {}
+    if rank == 0:
+        from bosot_b200 import hellinger
+
+        Xv = np.random.default_rng(6).random((20, DIM))
+        hsp = hellinger.HellingerSpace(gram, Xv, 100, dev)
+        st_e = hellinger.grams(sot.as_device_trees(ev4, dev), hsp)
+        st_c = hellinger.grams(d4, hsp)
+        Kh = {"K": torch.empty((C4_POOL, C4_EVAL), dtype=torch.float64, device=dev)}
+        ms_hg = timed(lambda: hellinger.grams(d4, hsp, check=False), 5, 3, collective=False)
+        ms_hp = timed(lambda: hellinger.pairs(st_c, st_e, hsp, 1.0, 0.5, out=Kh), 5, 3, collective=False)
+        dets = C4_POOL * C4_EVAL * 100
+        hell = dict(workload="hellinger_10k_x_50_S100_V20", gram_store_ms=ms_hg, pair_ms=ms_hp,
+                    pairs_per_s=C4_POOL * C4_EVAL / ((ms_hg + ms_hp) * 1e-3), determinants_per_s=dets / (ms_hp * 1e-3),
+                    pair_kernel_useful_fp64_tflops=dets * 2 * 1330.0 / (ms_hp * 1e-3) / 1e12,
+                    pair_kernel_frac_of_dfma_peak=dets * 2 * 1330.0 / (ms_hp * 1e-3) / 1e12 / fp64_tflops,
+                    note="20 x 20 LDL^T = 1330 FMA per determinant; shared-memory / shuffle wavefronts, not the fp64 pipe, bound the pair kernel (DESIGN.md 3.5)")
+        if world == 1 and not args.no_cpu_baseline:
+            import time as _time
+
+            from bosot_b200.encoding import decode_to_tuple
+            from oracle import ref_hellinger as rh
+
+            n_s = 12
+            te = [decode_to_tuple(r, gram) for r in ev4]
+            tc = [decode_to_tuple(r, gram) for r in ca4[:n_s]]
+            t0 = _time.perf_counter()
+            Kcpu = rh.K(tc, te, Xv, 100, DIM, 1.0, 0.5)
+            dt = _time.perf_counter() - t0
+            hell["cpu_port"] = dict(pairs_per_s=n_s * C4_EVAL / dt, cores=1, sample="first %d candidates x %d evaluated in %.1f s (NumPy slogdet)" % (n_s, C4_EVAL, dt),
+                                    gpu_matches_cpu_on_sample=bool(np.allclose(Kh["K"][:n_s].cpu().numpy(), Kcpu, rtol=1e-6)))
+
     peaks = measured_peaks()
     pairs = pool * N_EVAL
     value = pairs / (ms_step * 1e-3)
@@ -367,6 +400,7 @@ def main() -> None:
             roofline=roofline,
             cpu_baseline=cpu,
             c4_10k_x_50=c4,
+            hellinger_10k_x_50=hell,
         )
         print(json.dumps(line), flush=True)
     if world > 1:
