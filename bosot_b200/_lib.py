@@ -70,6 +70,7 @@ SIGNATURES = {
     "bosot_featurize": (C.c_int, [_P, C.c_int64, _G] + [_P] * 11 + [_P]),
     "bosot_eval_state_bytes": (C.c_size_t, [C.c_int]),
     "bosot_eval_build": (C.c_int, [_P, C.c_int, _G, _P, C.c_size_t, _P, _P]),
+    "bosot_eval_info": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int32), _P]),
     "bosot_sot_pairs_scratch_bytes": (C.c_size_t, [C.c_int64]),
     "bosot_sot_pairs": (C.c_int, [_P, C.c_int64, _G, _P, C.c_int, _D3, C.c_double, C.c_double, _P, _P, _P, C.c_int64, _P, _P, C.c_size_t, _P]),
     "bosot_posterior_acq": (

@@ -123,11 +123,11 @@ featurize_kernel(const uint8_t* __restrict__ trees, int64_t n_trees, bosot_gramm
 constexpr int kBuildThreads = 1024;
 
 __global__ void __launch_bounds__(kBuildThreads)
-eval_build_kernel(uint8_t* __restrict__ blob, EvalLayout L, int n_dim_cols,
+eval_build_kernel(uint8_t* __restrict__ blob, EvalLayout L, bosot_grammar g,
                   const uint8_t* __restrict__ n_nodes, const uint8_t* __restrict__ n_leaves,
                   const uint8_t* __restrict__ sub_n, const uint64_t* __restrict__ sub_id, const uint8_t* __restrict__ sub_cnt,
                   const uint8_t* __restrict__ path_n, const uint16_t* __restrict__ path_id, const uint8_t* __restrict__ path_cnt,
-                  const uint8_t* __restrict__ sym_cnt, int n_symbols, const double* __restrict__ dimvec) {
+                  const uint8_t* __restrict__ sym_cnt, const double* __restrict__ dimvec) {
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(blob + L.off_keys);
   uint2* range = reinterpret_cast<uint2*>(blob + L.off_range);
   uint32_t* post = reinterpret_cast<uint32_t*>(blob + L.off_post);
@@ -137,16 +137,41 @@ eval_build_kernel(uint8_t* __restrict__ blob, EvalLayout L, int n_dim_cols,
   uint32_t* cursor = reinterpret_cast<uint32_t*>(blob + L.off_cursor);
   const int E = L.n_eval;
   const int tid = threadIdx.x;
+  const int n_dim_cols = g.n_dim_cols, n_symbols = g.n_symbols;
 
+  // DIM_WISE column bookkeeping: block-major ("permuted") column order, see DimMeta
+  __shared__ DimMeta meta;
+  __shared__ uint8_t pcol[BOSOT_MAX_DIM_COLS];                 // permuted position -> reference column
+  __shared__ double states[BOSOT_MAX_DIM_COLS * kMaxStates];   // [permuted position][state]
   if (tid == 0) {
+    int8_t col_block[BOSOT_MAX_DIM_COLS], pos_of_col[BOSOT_MAX_DIM_COLS];
+    for (int c = 0; c < BOSOT_MAX_DIM_COLS; ++c) { col_block[c] = -1; pos_of_col[c] = -1; }
+    for (int b = 0; b < g.n_blocks; ++b) col_block[g.block_null_col[b]] = (int8_t)b;
+    for (int s = 0; s < n_symbols; ++s)
+      if (g.sym_block[s] >= 0 && g.sym_col[s] >= 0) col_block[g.sym_col[s]] = g.sym_block[s];
+    int j = 0;
+    for (int b = 0; b < g.n_blocks; ++b) {
+      meta.bbeg[b] = (uint8_t)j;
+      for (int c = 0; c < n_dim_cols; ++c)
+        if (col_block[c] == b) { pcol[j] = (uint8_t)c; pos_of_col[c] = (int8_t)j; ++j; }
+    }
+    for (int b = g.n_blocks; b < BOSOT_MAX_BLOCKS + 4; ++b) meta.bbeg[b] = (uint8_t)j;
+    meta.n_pcols = j;
+    for (int s = 0; s < BOSOT_MAX_SYMBOLS; ++s)
+      meta.sym_pos[s] = (s < n_symbols && g.sym_block[s] >= 0 && g.sym_col[s] >= 0) ? pos_of_col[g.sym_col[s]] : (int8_t)-1;
+    for (int b = 0; b < BOSOT_MAX_BLOCKS; ++b) {
+      meta.null_pos[b] = b < g.n_blocks ? pos_of_col[g.block_null_col[b]] : (int8_t)0;
+      meta.n_states[b] = 0;
+    }
+    meta.pad[0] = meta.pad[1] = meta.pad[2] = meta.pad[3] = 0;
     int* hdr = reinterpret_cast<int*>(blob);
     hdr[0] = E; hdr[1] = L.e_pad; hdr[2] = L.hash_cap; hdr[3] = L.n_slots; hdr[4] = n_dim_cols;
   }
+  for (int x = tid; x < BOSOT_MAX_DIM_COLS * kMaxStates; x += kBuildThreads) states[x] = 0.0;
   for (int s = tid; s < L.hash_cap; s += kBuildThreads) keys[s] = 0ULL;
   for (int s = tid; s < L.n_slots; s += kBuildThreads) { range[s] = make_uint2(0u, 0u); cursor[s] = 0u; }
   double* b_rsub = reinterpret_cast<double*>(blob + L.off_rsub);
   double* b_rpath = reinterpret_cast<double*>(blob + L.off_rpath);
-  uint8_t* symT = blob + L.off_symT;
   for (int e = tid; e < L.e_pad; e += kBuildThreads) {
     const int nn = e < E ? n_nodes[e] : 1, nl = e < E ? n_leaves[e] : 1;
     b_nn[e] = (uint8_t)nn;
@@ -154,15 +179,71 @@ eval_build_kernel(uint8_t* __restrict__ blob, EvalLayout L, int n_dim_cols,
     b_rsub[e] = 1.0 / (double)(nn ? nn : 1);
     b_rpath[e] = 1.0 / (double)(nl ? nl : 1);
   }
-  for (int x = tid; x < BOSOT_MAX_SYMBOLS * L.e_pad; x += kBuildThreads) {
-    const int s = x / L.e_pad, e = x % L.e_pad;
-    symT[x] = (s < n_symbols && e < E) ? sym_cnt[(size_t)e * n_symbols + s] : 0;
+  // packed transposed tables: word 32 q + l holds tree 64 q + l (low half) and tree 64 q + 32 + l (high half)
+  const int half = L.e_pad / 2;
+  uint32_t* symT2 = reinterpret_cast<uint32_t*>(blob + L.off_symT2);
+  uint32_t* nn2 = reinterpret_cast<uint32_t*>(blob + L.off_nn2);
+  for (int x = tid; x < BOSOT_MAX_SYMBOLS * half; x += kBuildThreads) {
+    const int s = x / half, w = x % half;
+    const int e_lo = 64 * (w >> 5) + (w & 31), e_hi = e_lo + 32;
+    const uint32_t lo = (s < n_symbols && e_lo < E) ? sym_cnt[(size_t)e_lo * n_symbols + s] : 0u;
+    const uint32_t hi = (s < n_symbols && e_hi < E) ? sym_cnt[(size_t)e_hi * n_symbols + s] : 0u;
+    symT2[x] = lo | (hi << 16);
   }
-  for (int x = tid; x < BOSOT_MAX_DIM_COLS * L.e_pad; x += kBuildThreads) {
-    const int c = x / L.e_pad, e = x % L.e_pad;
-    dimT[x] = (c < n_dim_cols && e < E) ? dimvec[(size_t)e * n_dim_cols + c] : 0.0;
+  for (int w = tid; w < half; w += kBuildThreads) {
+    const int e_lo = 64 * (w >> 5) + (w & 31), e_hi = e_lo + 32;
+    const uint32_t lo = e_lo < E ? n_nodes[e_lo] : 1u, hi = e_hi < E ? n_nodes[e_hi] : 1u;
+    nn2[w] = lo | (hi << 16);
   }
   __syncthreads();
+  for (int x = tid; x < BOSOT_MAX_DIM_COLS * L.e_pad; x += kBuildThreads) {
+    const int j = x / L.e_pad, e = x % L.e_pad;
+    dimT[x] = (j < meta.n_pcols && e < E) ? dimvec[(size_t)e * n_dim_cols + pcol[j]] : 0.0;
+  }
+  // distinct block vectors ("states") of the evaluated trees: warp b owns block b, lane s compares state s
+  uint8_t* sid8T = blob + L.off_sid8T;
+  for (int x = tid; x < BOSOT_MAX_BLOCKS * L.e_pad; x += kBuildThreads) sid8T[x] = 0;
+  __syncthreads();
+  {
+    const int b = tid >> 5, lane = tid & 31;
+    if (b < g.n_blocks) {
+      const int j0 = meta.bbeg[b], j1 = meta.bbeg[b + 1];
+      int ns = 0;
+      for (int e = 0; e < E; ++e) {
+        bool eq = lane < ns && lane < kMaxStates;
+        for (int j = j0; j < j1; ++j)
+          eq = eq && (__double_as_longlong(states[j * kMaxStates + lane]) ==
+                      __double_as_longlong(dimvec[(size_t)e * n_dim_cols + pcol[j]]));
+        const unsigned m = __ballot_sync(0xffffffffu, eq);
+        int sid;
+        if (m) {
+          sid = __ffs(m) - 1;
+        } else {
+          sid = ns;
+          if (ns < kMaxStates)
+            for (int j = j0 + lane; j < j1; j += 32) states[j * kMaxStates + ns] = dimvec[(size_t)e * n_dim_cols + pcol[j]];
+          if (ns <= kMaxStates) ++ns;  // saturates at kMaxStates + 1 = "too many"
+          __syncwarp();
+        }
+        if (lane == 0) sid8T[(size_t)b * L.e_pad + e] = (uint8_t)(8 * (sid < kMaxStates ? sid : 0));
+      }
+      if (lane == 0) meta.n_states[b] = (uint8_t)ns;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int ok = 1;
+    for (int b = 0; b < g.n_blocks; ++b) ok = ok && (meta.n_states[b] <= kMaxStates);
+    meta.use_states = ok;
+  }
+  __syncthreads();
+  {
+    double* stateP = reinterpret_cast<double*>(blob + L.off_stateP);
+    for (int x = tid; x < BOSOT_MAX_DIM_COLS * kMaxStates; x += kBuildThreads) stateP[x] = states[x];
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&meta);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(blob + L.off_meta);
+    for (int x = tid; x < (int)(sizeof(DimMeta) / 4); x += kBuildThreads) dst[x] = src[x];
+  }
 
   // pass 1: slot of every (tree, feature); count per slot (range.y)
   auto slot_of_sub = [&](uint64_t id) -> uint32_t {  // operator classes only (bit 63 set)
@@ -287,9 +368,27 @@ extern "C" int bosot_eval_build(const uint8_t* d_trees, int n_eval, const bosot_
       reinterpret_cast<double*>(b + S.dimvec), d_status);
   if (int rc = after_launch("featurize_kernel(eval)")) return rc;
   eval_build_kernel<<<1, kBuildThreads, 0, st>>>(
-      b, L, grammar->n_dim_cols, b + S.n_nodes, b + S.n_leaves, b + S.sub_n,
+      b, L, *grammar, b + S.n_nodes, b + S.n_leaves, b + S.sub_n,
       reinterpret_cast<const uint64_t*>(b + S.sub_id), b + S.sub_cnt, b + S.path_n,
-      reinterpret_cast<const uint16_t*>(b + S.path_id), b + S.path_cnt, b + S.sym_cnt, grammar->n_symbols,
+      reinterpret_cast<const uint16_t*>(b + S.path_id), b + S.path_cnt, b + S.sym_cnt,
       reinterpret_cast<const double*>(b + S.dimvec));
   return after_launch("eval_build_kernel");
+}
+
+extern "C" int bosot_eval_info(const void* d_blob, int n_eval, int32_t h_info[4], void* stream) {
+  if (!d_blob || !h_info) return set_error(BOSOT_EINVAL, "bosot_eval_info: null argument");
+  if (n_eval < 1 || n_eval > BOSOT_MAX_EVAL) return set_error(BOSOT_EINVAL, "bosot_eval_info: n_eval out of range");
+  const EvalLayout L = eval_layout(n_eval);
+  DimMeta m;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = cuda_check(cudaMemcpyAsync(&m, static_cast<const uint8_t*>(d_blob) + L.off_meta, sizeof(m), cudaMemcpyDeviceToHost, st),
+                          "cudaMemcpyAsync(DimMeta)")) return rc;
+  if (int rc = cuda_check(cudaStreamSynchronize(st), "cudaStreamSynchronize")) return rc;
+  int most = 0;
+  for (int b = 0; b < BOSOT_MAX_BLOCKS; ++b) most = m.n_states[b] > most ? m.n_states[b] : most;
+  h_info[0] = m.use_states;
+  h_info[1] = m.n_pcols;
+  h_info[2] = most;
+  h_info[3] = n_eval;
+  return BOSOT_OK;
 }

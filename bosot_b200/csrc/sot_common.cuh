@@ -134,9 +134,28 @@ __device__ __forceinline__ int scan_tree(uint8_t* rec, int n_symbols) {
 }
 
 // ---- evaluated-set blob layout (all offsets 16-byte aligned) ---------------------------
+// DIM_WISE bookkeeping written by eval_build_kernel.  The columns of the dim-wise vector are kept in
+// BLOCK-MAJOR order ("permuted position" j): block 0's columns (ascending reference column), block 1's, ...;
+// columns that belong to no block are identically zero for every tree and are dropped.  Inside a block the
+// evaluated trees take only a few distinct vectors ("states": a block is NULL or a normalised count vector
+// of its kinds); when every block has <= kMaxStates of them the pair kernel replaces the per-column L1 by
+// one table lookup per (pair, block).
+constexpr int kMaxStates = 32;
+struct DimMeta {
+  int32_t use_states;                    // 1: every block has <= kMaxStates distinct vectors
+  int32_t n_pcols;                       // number of permuted columns
+  uint8_t bbeg[BOSOT_MAX_BLOCKS + 4];    // block b = permuted positions bbeg[b] .. bbeg[b+1]-1
+  int8_t sym_pos[BOSOT_MAX_SYMBOLS];     // permuted position of a symbol's column, -1 = none
+  int8_t null_pos[BOSOT_MAX_BLOCKS];     // permuted position of NULL_b
+  uint8_t n_states[BOSOT_MAX_BLOCKS];    // distinct vectors per block (saturates at kMaxStates + 1)
+  uint8_t pad[4];
+};
+static_assert(sizeof(DimMeta) == 128, "DimMeta is staged with one 128-byte bulk copy");
+
 struct EvalLayout {
   int n_eval;     // E
-  int e_pad;      // E rounded up to 32; beyond 256 evaluated trees rounded up to 256 (whole register tiles)
+  int e_pad;      // E rounded up to 64 (lane l of a warp owns trees l + 32 r; two of them share a packed word);
+                  // beyond 256 evaluated trees rounded up to 256 (whole register tiles)
   int hash_cap;   // power of two >= 2 * 31 * E (load factor <= 0.5)
   int n_slots;    // hash_cap + 64 + 64*64 : unified slot space (hash | leaf symbol | path id)
   int max_post;   // 63 * E
@@ -147,8 +166,13 @@ struct EvalLayout {
   size_t off_nleaves;  // uint8  [e_pad]     PATHS total (leaves)
   size_t off_rsub;     // double [e_pad]     1 / nodes
   size_t off_rpath;    // double [e_pad]     1 / leaves
-  size_t off_symT;     // uint8  [BOSOT_MAX_SYMBOLS][e_pad]  leaf count per symbol, transposed
-  size_t off_dimT;     // double [BOSOT_MAX_DIM_COLS][e_pad]  transposed dim-wise matrix
+  size_t off_symT2;    // uint32 [BOSOT_MAX_SYMBOLS][e_pad/2]  leaf count per symbol, transposed and packed:
+                       //        word 32 q + l = count(tree 64 q + l) | count(tree 64 q + 32 + l) << 16
+  size_t off_nn2;      // uint32 [e_pad/2]   node totals, packed the same way
+  size_t off_meta;     // DimMeta
+  size_t off_stateP;   // double [BOSOT_MAX_DIM_COLS][kMaxStates]  value of permuted column j in state s of its block
+  size_t off_sid8T;    // uint8  [BOSOT_MAX_BLOCKS][e_pad]  8 * (state of tree e in block b)
+  size_t off_dimT;     // double [BOSOT_MAX_DIM_COLS][e_pad]  transposed dim-wise matrix, permuted column order
   size_t off_cursor;   // uint32 [n_slots]   build scratch
   size_t total;
 };
@@ -158,7 +182,7 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t
 __host__ __device__ inline EvalLayout eval_layout(int n_eval) {
   EvalLayout L;
   L.n_eval = n_eval;
-  L.e_pad = n_eval <= 256 ? ((n_eval + 31) & ~31) : ((n_eval + 255) & ~255);
+  L.e_pad = n_eval <= 256 ? ((n_eval + 63) & ~63) : ((n_eval + 255) & ~255);
   int cap = 64;
   while (cap < 2 * kMaxInternal * n_eval) cap <<= 1;
   L.hash_cap = cap;
@@ -172,7 +196,11 @@ __host__ __device__ inline EvalLayout eval_layout(int n_eval) {
   L.off_nleaves = o;   o = align16(o + (size_t)L.e_pad);
   L.off_rsub = o;      o = align16(o + sizeof(double) * (size_t)L.e_pad);
   L.off_rpath = o;     o = align16(o + sizeof(double) * (size_t)L.e_pad);
-  L.off_symT = o;      o = align16(o + (size_t)BOSOT_MAX_SYMBOLS * L.e_pad);
+  L.off_symT2 = o;     o = align16(o + sizeof(uint32_t) * (size_t)BOSOT_MAX_SYMBOLS * (L.e_pad / 2));
+  L.off_nn2 = o;       o = align16(o + sizeof(uint32_t) * (size_t)(L.e_pad / 2));
+  L.off_meta = o;      o = align16(o + sizeof(DimMeta));
+  L.off_stateP = o;    o = align16(o + sizeof(double) * (size_t)BOSOT_MAX_DIM_COLS * kMaxStates);
+  L.off_sid8T = o;     o = align16(o + (size_t)BOSOT_MAX_BLOCKS * L.e_pad);
   L.off_dimT = o;      o = align16(o + sizeof(double) * (size_t)BOSOT_MAX_DIM_COLS * L.e_pad);
   L.off_cursor = o;    o = align16(o + sizeof(uint32_t) * (size_t)L.n_slots);
   L.total = o;

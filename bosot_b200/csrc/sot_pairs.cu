@@ -50,28 +50,46 @@ struct PairParams {
   const uint8_t* recs;  // compact records written by scan_kernel: [n_cand][kScanBytes]
 };
 
-// per-warp shared memory: candidate dim-wise vector, accumulators, symbol counts
-__host__ __device__ inline size_t pair_warp_smem(int e_pad) {
-  return sizeof(double) * BOSOT_MAX_DIM_COLS + sizeof(uint32_t) * (size_t)e_pad +
-         sizeof(uint32_t) * (BOSOT_MAX_SYMBOLS + BOSOT_MAX_BLOCKS);
+// per-warp shared memory: candidate dim-wise vector, block-state distance table, walk segments, accumulators, symbol counts
+struct WarpLayout {
+  size_t off_tab, off_slot, off_acc, off_scnt, total;
+};
+__host__ __device__ inline WarpLayout warp_layout(int e_pad, int n_dim_cols, int n_blocks) {
+  WarpLayout W;
+  size_t o = sizeof(double) * (size_t)((n_dim_cols + 1) & ~1);           // avec [n_pcols]
+  W.off_tab = o;   o += sizeof(double) * (size_t)kMaxStates * n_blocks;  // tab [n_blocks][kMaxStates]
+  W.off_slot = o;  o += sizeof(uint2) * 32;                              // segments of the flattened postings walk
+  W.off_acc = o;   o += sizeof(uint32_t) * (size_t)e_pad;                // M_sub(ops) | M_path << 16 per e
+  W.off_scnt = o;  o += sizeof(uint32_t) * (BOSOT_MAX_SYMBOLS + BOSOT_MAX_BLOCKS);
+  W.total = align16(o);
+  return W;
 }
 
-// CTA-wide staged copy of the evaluated set's dense tables (section sizes are multiples of 16 bytes)
+// CTA-wide staged copy of the evaluated set's dense tables (section sizes are multiples of 16 bytes).
+// The DIM_WISE section holds either the block-state tables (stateP + sid8T) or, when a block has more than
+// kMaxStates distinct vectors, the dense transposed matrix; it is sized for the larger of the two.
 struct StageLayout {
-  size_t off_dimT, off_rsub, off_rpath, off_symT, off_nn, off_nl, total;
-  uint32_t b_dimT, b_r, b_symT, b_n;
+  size_t off_meta, off_dim, off_sid, off_rsub, off_rpath, off_symT2, off_nn2, off_nn, off_nl, total;
+  uint32_t b_meta, b_state, b_sid, b_dimT, b_r, b_symT2, b_nn2, b_n;
 };
-__host__ __device__ inline StageLayout stage_layout(int e_pad, int n_dim_cols, int n_symbols) {
+__host__ __device__ inline StageLayout stage_layout(int e_pad, int n_dim_cols, int n_symbols, int n_blocks) {
   StageLayout S;
+  S.b_meta = (uint32_t)sizeof(DimMeta);
+  S.b_state = (uint32_t)(sizeof(double) * (size_t)n_dim_cols * kMaxStates);
+  S.b_sid = (uint32_t)((size_t)n_blocks * e_pad);
   S.b_dimT = (uint32_t)(sizeof(double) * (size_t)n_dim_cols * e_pad);
   S.b_r = (uint32_t)(sizeof(double) * (size_t)e_pad);
-  S.b_symT = (uint32_t)((size_t)n_symbols * e_pad);
+  S.b_symT2 = (uint32_t)(sizeof(uint32_t) * (size_t)n_symbols * (e_pad / 2));
+  S.b_nn2 = (uint32_t)(sizeof(uint32_t) * (size_t)(e_pad / 2));
   S.b_n = (uint32_t)e_pad;
   size_t o = 16;  // mbarrier
-  S.off_dimT = o;  o += S.b_dimT;
+  S.off_meta = o;  o += S.b_meta;
+  S.off_dim = o;   S.off_sid = o + S.b_state;
+  o += (S.b_state + S.b_sid > S.b_dimT) ? (S.b_state + S.b_sid) : S.b_dimT;
   S.off_rsub = o;  o += S.b_r;
   S.off_rpath = o; o += S.b_r;
-  S.off_symT = o;  o += S.b_symT;
+  S.off_symT2 = o; o += S.b_symT2;
+  S.off_nn2 = o;   o += S.b_nn2;
   S.off_nn = o;    o += S.b_n;
   S.off_nl = o;    o += S.b_n;
   S.total = align16(o);
@@ -129,44 +147,102 @@ scan_kernel(const uint8_t* __restrict__ trees, int64_t n_trees, int n_symbols, u
 }
 
 // ---- launch 2: warp-per-tree pairs ----------------------------------------------------------
+// exp_nonpos (fast_math.cuh) on G arguments at once: the same operations in the same order (bit-identical
+// results), but every coefficient is fetched once per group and the G Horner chains interleave.
+template <int G>
+__device__ __forceinline__ void exp_nonpos_group(double (&x)[G]) {
+  double r[G], q[G];
+  int n[G];
+  {
+    const double lo = c_exp[15], l2e = c_exp[0], magic = c_exp[1], ln2h = c_exp[2], ln2l = c_exp[3], c13 = c_exp[4];
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const double v = x[i] < lo ? lo : x[i];  // NaN stays NaN
+      const double t = fma(v, l2e, magic);
+      n[i] = __double2loint(t);
+      const double nf = t - magic;
+      r[i] = fma(nf, ln2l, fma(nf, ln2h, v));
+      q[i] = c13;
+    }
+  }
+#pragma unroll
+  for (int k = 5; k <= 14; ++k) {
+    const double ck = c_exp[k];
+#pragma unroll
+    for (int i = 0; i < G; ++i) q[i] = fma(q[i], r[i], ck);
+  }
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    double v = fma(q[i], r[i], 0.5);
+    v = fma(v, r[i], 1.0);
+    v = fma(v, r[i], 1.0);
+    const int n1 = n[i] >> 1, n2 = n[i] - n1;
+    x[i] = (v * __hiloint2double((1023 + n1) << 20, 0)) * __hiloint2double((1023 + n2) << 20, 0);
+  }
+}
+
+// exact uint32 -> double for m < 2^32 without the conversion pipe: 2^52 + m is exact, subtract 2^52
+__device__ __forceinline__ double u32_to_f64(uint32_t m) {
+  return __hiloint2double(0x43300000, (int)m) - 4503599627370496.0;
+}
+
+__device__ double g_frac[33 * 33];  // g_frac[c * 33 + t] = (double)c / (double)t (correctly rounded, filled by the host)
+
 template <int R, bool kExtra>  // R: evaluated trees per lane per tile; kExtra: also write D and/or Df
 __global__ void __launch_bounds__(kMaxPairWarps * 32, 1)
 sot_pair_kernel(PairParams p, bosot_grammar g) {
+  constexpr int RP = (R + 1) / 2;  // packed pairs of evaluated trees per lane
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int n_warps = blockDim.x >> 5;
   const int E = p.L.n_eval;
   const int e_pad = p.L.e_pad;
-  const int F = g.n_dim_cols;
+  const int half_pad = e_pad >> 1;
   const unsigned full = 0xffffffffu;
+  const unsigned lt_mask = (1u << lane) - 1u, le_mask = (2u << lane) - 1u;
 
   // ---- stage the evaluated set's dense tables once per (persistent) CTA: TMA bulk copies -> mbarrier
-  const StageLayout S = stage_layout(e_pad, F, g.n_symbols);
+  const StageLayout S = stage_layout(e_pad, g.n_dim_cols, g.n_symbols, g.n_blocks);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   if (threadIdx.x == 0) mbar_init(bar, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, S.b_dimT + 2 * S.b_r + S.b_symT + 2 * S.b_n);
-    tma_bulk_g2s(smem + S.off_dimT, p.blob + p.L.off_dimT, S.b_dimT, bar);
+    const int states = __ldg(reinterpret_cast<const int*>(p.blob + p.L.off_meta));  // DimMeta::use_states
+    mbar_expect_tx(bar, S.b_meta + (states ? S.b_state + S.b_sid : S.b_dimT) + 2 * S.b_r + S.b_symT2 + S.b_nn2 + 2 * S.b_n);
+    tma_bulk_g2s(smem + S.off_meta, p.blob + p.L.off_meta, S.b_meta, bar);
+    if (states) {
+      tma_bulk_g2s(smem + S.off_dim, p.blob + p.L.off_stateP, S.b_state, bar);
+      tma_bulk_g2s(smem + S.off_sid, p.blob + p.L.off_sid8T, S.b_sid, bar);
+    } else {
+      tma_bulk_g2s(smem + S.off_dim, p.blob + p.L.off_dimT, S.b_dimT, bar);
+    }
     tma_bulk_g2s(smem + S.off_rsub, p.blob + p.L.off_rsub, S.b_r, bar);
     tma_bulk_g2s(smem + S.off_rpath, p.blob + p.L.off_rpath, S.b_r, bar);
-    tma_bulk_g2s(smem + S.off_symT, p.blob + p.L.off_symT, S.b_symT, bar);
+    tma_bulk_g2s(smem + S.off_symT2, p.blob + p.L.off_symT2, S.b_symT2, bar);
+    tma_bulk_g2s(smem + S.off_nn2, p.blob + p.L.off_nn2, S.b_nn2, bar);
     tma_bulk_g2s(smem + S.off_nn, p.blob + p.L.off_nnodes, S.b_n, bar);
     tma_bulk_g2s(smem + S.off_nl, p.blob + p.L.off_nleaves, S.b_n, bar);
   }
-  const double* dimT = reinterpret_cast<const double*>(smem + S.off_dimT);
+  const DimMeta* meta = reinterpret_cast<const DimMeta*>(smem + S.off_meta);
+  const double* stateP = reinterpret_cast<const double*>(smem + S.off_dim);  // [n_pcols][kMaxStates]   (state mode)
+  const double* dimT = stateP;                                               // [n_pcols][e_pad]        (dense mode)
+  const uint8_t* sid8T = smem + S.off_sid;
   const double* e_rsub = reinterpret_cast<const double*>(smem + S.off_rsub);
   const double* e_rpath = reinterpret_cast<const double*>(smem + S.off_rpath);
-  const uint8_t* symT = smem + S.off_symT;
+  const uint32_t* symT2 = reinterpret_cast<const uint32_t*>(smem + S.off_symT2);
+  const uint32_t* e_nn2 = reinterpret_cast<const uint32_t*>(smem + S.off_nn2);
   const uint8_t* e_nn = smem + S.off_nn;
   const uint8_t* e_nl = smem + S.off_nl;
 
-  uint8_t* wbase = smem + S.total + (size_t)warp * pair_warp_smem(e_pad);
-  double* avec = reinterpret_cast<double*>(wbase);                         // candidate DIM_WISE vector
-  uint32_t* acc = reinterpret_cast<uint32_t*>(avec + BOSOT_MAX_DIM_COLS);  // M_sub(ops) | M_path << 16 per e
-  uint32_t* scnt = acc + e_pad;                                            // leaf count per symbol
-  uint32_t* btot = scnt + BOSOT_MAX_SYMBOLS;                               // leaf count per block
+  const WarpLayout W = warp_layout(e_pad, g.n_dim_cols, g.n_blocks);
+  uint8_t* wbase = smem + S.total + (size_t)warp * W.total;
+  double* avec = reinterpret_cast<double*>(wbase);                   // candidate DIM_WISE vector, permuted column order
+  double* tab = reinterpret_cast<double*>(wbase + W.off_tab);        // tab[b][s] = L1(candidate block b, state s)
+  uint2* slot = reinterpret_cast<uint2*>(wbase + W.off_slot);        // (postings begin - flattened start, candidate count)
+  uint32_t* acc = reinterpret_cast<uint32_t*>(wbase + W.off_acc);    // M_sub(ops) | M_path << 16 per e
+  uint32_t* scnt = reinterpret_cast<uint32_t*>(wbase + W.off_scnt);  // leaf count per symbol
+  uint32_t* btot = scnt + BOSOT_MAX_SYMBOLS;                         // leaf count per block
 
   const unsigned long long* keys = reinterpret_cast<const unsigned long long*>(p.blob + p.L.off_keys);
   const uint2* range = reinterpret_cast<const uint2*>(p.blob + p.L.off_range);
@@ -191,6 +267,8 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   Slice nxt;
   if (t < p.n_cand) nxt = load_slice(t);
   mbar_wait(bar, 0);  // tables landed (the copy overlapped the first record load)
+  const bool use_states = meta->use_states != 0;
+  const int n_pcols = meta->n_pcols;
 
   for (; t < p.n_cand; t += stride) {
     const Slice cur = nxt;
@@ -213,11 +291,9 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
 
     __syncwarp();
 #pragma unroll 1
-    for (int e = lane; e < e_pad; e += 32) acc[e] = 0u;
+    for (int e = 2 * lane; e < e_pad; e += 64) *reinterpret_cast<uint2*>(acc + e) = make_uint2(0u, 0u);
 #pragma unroll 1
     for (int s = lane; s < BOSOT_MAX_SYMBOLS + BOSOT_MAX_BLOCKS; s += 32) scnt[s] = 0u;
-#pragma unroll 1
-    for (int c = lane; c < F; c += 32) avec[c] = 0.0;
     __syncwarp();
 
     // leaves: symbol multiplicities (SUBTREES leaf classes, DIM_WISE) and PATHS (key = symbol * 64 + code)
@@ -253,22 +329,25 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     }
     __syncwarp();
 
-    // candidate DIM_WISE vector from the symbol counts (optimal_transport_mappings.py:88-108)
+    // candidate DIM_WISE vector from the symbol counts (optimal_transport_mappings.py:88-108); count / total comes
+    // from the table of correctly rounded quotients (== float(a) / float(b)); every permuted column is written
 #pragma unroll 1
     for (int s = lane; s < g.n_symbols; s += 32) {
-      const int b = g.sym_block[s], c = g.sym_col[s];
-      if (b >= 0 && c >= 0) {
+      const int b = g.sym_block[s], j = meta->sym_pos[s];
+      if (b >= 0 && j >= 0) {
         const uint32_t tot = btot[b];
-        avec[c] = tot ? (double)scnt[s] / (double)tot : 0.0;
+        avec[j] = tot ? __ldg(&g_frac[scnt[s] * 33u + tot]) : 0.0;
       }
     }
-    if (lane < g.n_blocks) avec[g.block_null_col[lane]] = btot[lane] == 0u ? 1.0 : 0.0;
+    if (lane < g.n_blocks) avec[meta->null_pos[lane]] = btot[lane] == 0u ? 1.0 : 0.0;
 
-    // Walk the postings of all matched features as ONE flattened list: an exclusive scan of the list
-    // lengths over the lanes gives every feature its segment; in each round lane j takes posting
-    // q = 32 * round + j and finds its feature by a 5-step binary search over the segment starts
-    // (register shuffles).  Full rounds instead of one mostly empty round per feature; postings of
-    // different features may hit the same evaluated tree, hence the shared-memory atomic.
+    // Walk the postings of all matched features as ONE flattened list: an exclusive scan of the list lengths
+    // over the lanes gives every feature its segment [start, start + len); the non-empty segments are compacted
+    // into slot[0..) in lane order (= increasing start).  In each round lane j takes posting q = 32 * round + j;
+    // its segment is found without a search: the lanes whose segment starts inside this round set bit
+    // (start - q0) of a mask (warp OR-reduction), and the number of set bits at or below j, plus the number
+    // of segments that started in earlier rounds, is the segment's ordinal.  Postings of different features
+    // may hit the same evaluated tree, hence the shared-memory atomic.
     auto walk = [&](uint2 r, uint32_t cnt_a, uint32_t Ta, int shift) {
       uint32_t inc = r.y;
 #pragma unroll
@@ -277,86 +356,144 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
         if (lane >= o) inc += v;
       }
       const uint32_t total = __shfl_sync(full, inc, 31);
+      if (total == 0u) return;
       const uint32_t start = inc - r.y;
+      const bool ne = r.y != 0u;
+      const unsigned ne_mask = __ballot_sync(full, ne);
+      if (ne) slot[__popc(ne_mask & lt_mask)] = make_uint2(r.x - start, cnt_a);
+      __syncwarp();
+      uint32_t before = 0u;  // segments that start before this round
 #pragma unroll 1
       for (uint32_t q0 = 0; q0 < total; q0 += 32) {
+        const uint32_t rel = start - q0;
+        const uint32_t m = __reduce_or_sync(full, (ne && rel < 32u) ? (1u << rel) : 0u);
+        const uint32_t ord = before + (uint32_t)__popc(m & le_mask) - 1u;
+        before += (uint32_t)__popc(m);
         const uint32_t q = q0 + lane;
-        int k = 0;  // largest lane whose segment starts at or before q
-#pragma unroll
-        for (int step = 16; step; step >>= 1) {
-          const uint32_t sk = __shfl_sync(full, start, k + step);
-          if (sk <= q) k += step;
-        }
-        const uint32_t beg = __shfl_sync(full, r.x, k);
-        const uint32_t st = __shfl_sync(full, start, k);
-        const uint32_t ca = __shfl_sync(full, cnt_a, k);
         if (q < total) {
-          const uint32_t pq = __ldg(&post[beg + (q - st)]);
+          const uint2 sl = slot[ord];
+          const uint32_t pq = __ldg(&post[sl.x + q]);
           const uint32_t e = pq & 0xffffu, cb = (pq >> 16) & 0xffu, Tb = pq >> 24;
-          atomicAdd(&acc[e], min(ca * Tb, cb * Ta) << shift);
+          atomicAdd(&acc[e], min(sl.y * Tb, cb * Ta) << shift);
         }
       }
+      __syncwarp();
     };
     walk(r_int, (uint32_t)__popc(m_id), (uint32_t)nn, 0);
     walk(r_pid, (uint32_t)__popc(m_pid), (uint32_t)nl, 16);
+
+    // block-state distance table: lane s holds state s of every block
+    if (use_states) {
+#pragma unroll 1
+      for (int b = 0; b < g.n_blocks; ++b) {
+        double sum = 0.0;
+#pragma unroll 1
+        for (int j = meta->bbeg[b]; j < meta->bbeg[b + 1]; ++j) sum += fabs(avec[j] - stateP[j * kMaxStates + lane]);
+        tab[b * kMaxStates + lane] = sum;
+      }
+    }
     __syncwarp();
 
     // ---- phase C: register tiles of R evaluated trees per lane (tree e = e0 + lane + 32 r)
     const double rTa_sub = c_recip[nn], rTa_path = c_recip[nl];
     for (int e0 = 0; e0 < E; e0 += 32 * R) {
       const int eb = e0 + lane;  // e_pad is a whole number of tiles: eb + 32 r < e_pad, padded arrays stay in bounds
-      uint32_t msub[R];
+      uint32_t msub2[RP];
       double ddim[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        msub[r] = 0u;
-        ddim[r] = 0.0;
-      }
-      // SUBTREES, leaf classes: sum over the candidate's distinct symbols of min(ca * Tb, cb * Ta)
+      for (int q = 0; q < RP; ++q) msub2[q] = 0u;
+#pragma unroll
+      for (int r = 0; r < R; ++r) ddim[r] = 0.0;
+      // SUBTREES, leaf classes: sum over the candidate's distinct symbols of min(ca * Tb, cb * Ta), two evaluated
+      // trees per 32-bit word (all products and sums stay below 2^16: ca, cb <= 32, Ta, Tb <= 63)
       {
-        const uint8_t* nnp = e_nn + eb;
+        const int wb = (e0 >> 1) + lane;
+        uint32_t tb2[RP];
+#pragma unroll
+        for (int q = 0; q < RP; ++q) tb2[q] = e_nn2[wb + 32 * q];
         for (unsigned todo = sym_leads; todo;) {
           const int src = __ffs(todo) - 1;
           todo &= todo - 1;
           const uint32_t s = __shfl_sync(full, sym, src);
           const uint32_t ca = __shfl_sync(full, cnt_sym, src);
-          const uint8_t* col = symT + s * (uint32_t)e_pad + eb;
+          const uint32_t* col = symT2 + s * (uint32_t)half_pad + wb;
 #pragma unroll
-          for (int r = 0; r < R; ++r) msub[r] += min(ca * (uint32_t)nnp[32 * r], (uint32_t)col[32 * r] * (uint32_t)nn);
+          for (int q = 0; q < RP; ++q) msub2[q] += __vminu2(ca * tb2[q], col[32 * q] * (uint32_t)nn);
         }
       }
-      // DIM_WISE: dense L1 over the d * (kinds + 1) columns, column-outer so the candidate value is read once
-      {
-        const double* col = dimT + eb;
-#pragma unroll 2
-        for (int c = 0; c < F; ++c, col += e_pad) {
-          const double a = avec[c];
+      // DIM_WISE: per block, then across blocks (the same grouping in both modes, so they agree bit for bit)
+      if (use_states) {
+        const uint8_t* sp = sid8T + eb;
+        const uint8_t* tb = reinterpret_cast<const uint8_t*>(tab);
+#pragma unroll 1
+        for (int b = 0; b < g.n_blocks; ++b, sp += e_pad, tb += 8 * kMaxStates) {
 #pragma unroll
-          for (int r = 0; r < R; ++r) ddim[r] += fabs(a - col[32 * r]);
+          for (int r = 0; r < R; ++r) ddim[r] += *reinterpret_cast<const double*>(tb + sp[32 * r]);
         }
-      }
+      } else {
+#pragma unroll 1
+        for (int b = 0; b < g.n_blocks; ++b) {
+          double part[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int e = eb + 32 * r;
-        if (e < E) {
-          const uint32_t a = acc[e];
-          const uint32_t m_sub = msub[r] + (a & 0xffffu), m_path = a >> 16;
-          const uint32_t tb_sub = e_nn[e], tb_path = e_nl[e];
-          // 2 - 2*M/(Ta*Tb); exactly 0 when the histograms coincide; (1/Ta)*(1/Tb) first keeps D(a,b) == D(b,a) bitwise
-          const double d_sub = (m_sub == (uint32_t)nn * tb_sub)
-                                   ? 0.0 : fma(-2.0, (double)m_sub * (rTa_sub * e_rsub[e]), 2.0);
-          const double d_path = (m_path == (uint32_t)nl * tb_path)
-                                    ? 0.0 : fma(-2.0, (double)m_path * (rTa_path * e_rpath[e]), 2.0);
-          // sum_f w_f * D_f in feature_type_list order (kernel_kernel_grammar_tree.py:159-161)
-          const double d = __dadd_rn(__dadd_rn(__dmul_rn(p.w_dim, ddim[r]), __dmul_rn(p.w_path, d_path)),
-                                     __dmul_rn(p.w_sub, d_sub));
-          if (kExtra) {
-            if (p.Df) { p.Df[row + e] = ddim[r]; p.Df[plane + row + e] = d_path; p.Df[2 * plane + row + e] = d_sub; }
-            if (p.D) p.D[row + e] = d;
+          for (int r = 0; r < R; ++r) part[r] = 0.0;
+#pragma unroll 1
+          for (int j = meta->bbeg[b]; j < meta->bbeg[b + 1]; ++j) {
+            const double a = avec[j];
+            const double* col = dimT + (size_t)j * e_pad + eb;
+#pragma unroll
+            for (int r = 0; r < R; ++r) part[r] += fabs(a - col[32 * r]);
           }
-          if (p.K) p.K[row + e] = p.variance * exp_nonpos(d * p.neg_inv_lsq);
-        } else if (p.K && e < p.ld) {
-          p.K[row + e] = 0.0;  // padding columns of the Gram row stay finite (the posterior kernel may read them)
+#pragma unroll
+          for (int r = 0; r < R; ++r) ddim[r] += part[r];
+        }
+      }
+      // epilogue in groups of up to 4 trees per lane: distances, weighted sum, Gram entry
+      const uint32_t* accp = acc + eb;
+      const uint8_t* nnp = e_nn + eb;
+      const uint8_t* nlp = e_nl + eb;
+      const double* rsp = e_rsub + eb;
+      const double* rpp = e_rpath + eb;
+#pragma unroll
+      for (int r0 = 0; r0 < R; r0 += 4) {
+        constexpr int kG = 4;
+        double x[kG];
+#pragma unroll
+        for (int i = 0; i < kG; ++i) {
+          const int r = r0 + i;
+          if (r < R) {
+            const uint32_t a = accp[32 * r];
+            const uint32_t m_sub = ((msub2[r >> 1] >> (16 * (r & 1))) & 0xffffu) + (a & 0xffffu), m_path = a >> 16;
+            const uint32_t tb_sub = nnp[32 * r], tb_path = nlp[32 * r];
+            // 2 - 2*M/(Ta*Tb); exactly 0 when the histograms coincide; (1/Ta)*(1/Tb) first keeps D(a,b) == D(b,a) bitwise
+            double d_sub = fma(-2.0, u32_to_f64(m_sub) * (rTa_sub * rsp[32 * r]), 2.0);
+            double d_path = fma(-2.0, u32_to_f64(m_path) * (rTa_path * rpp[32 * r]), 2.0);
+            d_sub = (m_sub == (uint32_t)nn * tb_sub) ? 0.0 : d_sub;
+            d_path = (m_path == (uint32_t)nl * tb_path) ? 0.0 : d_path;
+            // sum_f w_f * D_f in feature_type_list order (kernel_kernel_grammar_tree.py:159-161)
+            const double d = __dadd_rn(__dadd_rn(__dmul_rn(p.w_dim, ddim[r]), __dmul_rn(p.w_path, d_path)),
+                                       __dmul_rn(p.w_sub, d_sub));
+            if (kExtra) {
+              const int e = eb + 32 * r;
+              if (e < E) {
+                if (p.Df) { p.Df[row + e] = ddim[r]; p.Df[plane + row + e] = d_path; p.Df[2 * plane + row + e] = d_sub; }
+                if (p.D) p.D[row + e] = d;
+              }
+            }
+            x[i] = d * p.neg_inv_lsq;
+          } else {
+            x[i] = 0.0;
+          }
+        }
+        if (p.K) {
+          exp_nonpos_group<kG>(x);
+#pragma unroll
+          for (int i = 0; i < kG; ++i) {
+            const int r = r0 + i, e = eb + 32 * r;
+            if (r < R) {
+              if (e < E) p.K[row + e] = p.variance * x[i];
+              else if (e < p.ld) p.K[row + e] = 0.0;  // padding columns of the Gram row stay finite (the posterior kernel may read them)
+            }
+          }
         }
       }
     }
@@ -373,6 +510,10 @@ static int ensure_recip_table() {
   h[0] = 0.0;
   for (int t = 1; t < 64; ++t) h[t] = 1.0 / (double)t;
   if (int rc = cuda_check(cudaMemcpyToSymbol(c_recip, h, sizeof(h)), "cudaMemcpyToSymbol(c_recip)")) return rc;
+  static double frac[33 * 33];  // count / total like the reference's float(a) / float(b) (optimal_transport_mappings.py:104-106)
+  for (int c = 0; c < 33; ++c)
+    for (int t = 0; t < 33; ++t) frac[c * 33 + t] = t ? (double)c / (double)t : 0.0;
+  if (int rc = cuda_check(cudaMemcpyToSymbol(g_frac, frac, sizeof(frac)), "cudaMemcpyToSymbol(g_frac)")) return rc;
   if (dev < 64) g_recip_ready[dev] = true;
   return BOSOT_OK;
 }
@@ -428,17 +569,18 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   // launch 2: pairs.  One persistent CTA per SM; small pools shrink the CTA so that every SM gets warps.
   int warps = kMaxPairWarps;
   while (warps > 1 && (n_cand + warps - 1) / warps < sms) warps >>= 1;
-  const StageLayout S = stage_layout(p.L.e_pad, grammar->n_dim_cols, grammar->n_symbols);
+  const StageLayout S = stage_layout(p.L.e_pad, grammar->n_dim_cols, grammar->n_symbols, grammar->n_blocks);
+  const size_t per_warp = warp_layout(p.L.e_pad, grammar->n_dim_cols, grammar->n_blocks).total;
   const size_t smem_cap = 220 * 1024;
-  size_t smem = S.total + (size_t)warps * pair_warp_smem(p.L.e_pad);
+  size_t smem = S.total + (size_t)warps * per_warp;
   while (smem > smem_cap && warps > 1) {
     warps >>= 1;
-    smem = S.total + (size_t)warps * pair_warp_smem(p.L.e_pad);
+    smem = S.total + (size_t)warps * per_warp;
   }
   if (smem > smem_cap) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: n_eval too large for shared memory");
 
   const bool extra = d_D != nullptr || d_Df != nullptr;
-  const int rounds = p.L.e_pad / 32;
+  const int rounds = (n_eval + 31) / 32;  // evaluated trees per lane; beyond 256 trees: tiles of 256 (e_pad is a multiple of 256)
   const int R = rounds < kMaxR ? rounds : kMaxR;
   using KernelFn = void (*)(PairParams, bosot_grammar);
   static const KernelFn table[kMaxR][2] = {

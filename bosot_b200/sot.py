@@ -142,6 +142,14 @@ class EvalState:
         _lib.check(rc, "eval_build")
         _raise_on_bad_trees(status, "evaluated set")
 
+    def info(self) -> Dict[str, int]:
+        """Diagnostics (C-ABI ``bosot_eval_info``): whether DIM_WISE goes through the block-state tables."""
+        h = (C.c_int32 * 4)()
+        with torch.cuda.device(self.trees.device):
+            rc = _lib.load().bosot_eval_info(self.blob.data_ptr(), self.n_eval, h, _stream(self.trees.device))
+        _lib.check(rc, "eval_info")
+        return {"dim_wise_states": int(h[0]), "dim_wise_columns": int(h[1]), "max_states_per_block": int(h[2]), "n_eval": int(h[3])}
+
 
 # ---------------------------------------------------------------------------------- pairs
 def sot_pairs(

@@ -117,12 +117,18 @@ int bosot_featurize(const uint8_t* d_trees, int64_t n_trees, const bosot_grammar
  * bosot_eval_state_bytes: size of the opaque device blob for E trees.
  * bosot_eval_build: featurises the E trees and builds, inside the blob, a hash table
  * canonical-class-id -> postings (e, count, total), direct tables for leaf symbols and
- * reduced paths, and the transposed dim-wise matrix.  d_status: int32[E].
+ * reduced paths, the transposed dim-wise matrix and the per-block tables of distinct dim-wise
+ * vectors ("states").  d_status: int32[E].
  */
 #define BOSOT_MAX_EVAL 4095
 size_t bosot_eval_state_bytes(int n_eval);
 int bosot_eval_build(const uint8_t* d_trees, int n_eval, const bosot_grammar* grammar,
                      void* d_blob, size_t blob_bytes, int32_t* d_status, void* stream);
+/* Diagnostics of a built blob (synchronises the stream): h_info[0] = 1 if the pair kernel evaluates DIM_WISE
+ * through the block-state tables (every block of input dimensions takes <= 32 distinct vectors over the
+ * evaluated trees), 0 = dense column loop; h_info[1] = dim-wise columns that belong to a block;
+ * h_info[2] = largest number of distinct vectors in one block (33 = more than 32); h_info[3] = n_eval. */
+int bosot_eval_info(const void* d_blob, int n_eval, int32_t h_info[4], void* stream);
 
 /* ---- SOT pair kernel ------------------------------------------------------------
  * For every candidate tree c (row) and evaluated tree e (column):

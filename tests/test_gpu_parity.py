@@ -309,6 +309,33 @@ def test_large_and_odd_evaluated_sets(n_eval):
     np.testing.assert_allclose(ei.cpu().numpy()[idx], ref["acq"], rtol=1e-6, atol=1e-12)
 
 
+def test_dim_wise_state_tables_and_dense_columns_agree():
+    """DIM_WISE has two evaluation modes in the pair kernel: per-block tables over the distinct block vectors of the
+    evaluated set (<= 32 per block) and the dense column loop (more).  Both against the oracle, and against each
+    other bit for bit (D(A, B) computed with B as the evaluated set must equal D(B, A) transposed)."""
+    gen, d = "CKSWithRQSearchSpace", 1  # one block with four kinds: deep trees give many distinct count vectors
+    gram = Grammar.get(gen, d)
+    rng = np.random.default_rng(11)
+    big = [rn.random_stress_tree(rng, gram.symbols, max_depth=5, p_leaf=0.15) for _ in range(230)]
+    small = [rn.random_stress_tree(rng, gram.symbols, max_depth=2) for _ in range(40)]
+    XB, XS = sot.as_device_trees(encode(big, gram), DEV), sot.as_device_trees(encode(small, gram), DEV)
+    st_big, st_small = sot.EvalState(XB, gram), sot.EvalState(XS, gram)
+    assert st_big.info()["dim_wise_states"] == 0 and st_big.info()["max_states_per_block"] == 33
+    assert st_small.info()["dim_wise_states"] == 1 and 1 <= st_small.info()["max_states_per_block"] <= 32
+    w = np.array([0.2, 0.5, 0.3])
+    a = sot.sot_pairs(XS, st_big, w, 1.3, 0.8, want=("K", "D", "Df"))    # dense columns
+    b = sot.sot_pairs(XB, st_small, w, 1.3, 0.8, want=("K", "D", "Df"))  # state tables
+    for key in ("K", "D"):
+        assert np.array_equal(a[key].cpu().numpy(), b[key].cpu().numpy().T), key
+    assert np.array_equal(a["Df"].cpu().numpy(), b["Df"].cpu().numpy().transpose(0, 2, 1))
+    np.testing.assert_allclose(a["Df"].cpu().numpy(), rn.per_feature_distances(small, big, gen, d), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(b["Df"].cpu().numpy(), rn.per_feature_distances(big, small, gen, d), rtol=0, atol=1e-12)
+    # self distances in both modes: exact zeros on the diagonal, bitwise symmetric
+    for X, st in ((XB, st_big), (XS, st_small)):
+        D = sot.sot_pairs(X, st, w, 1.3, 0.8, want=("D",))["D"].cpu().numpy()
+        assert np.all(np.diag(D) == 0.0) and np.array_equal(D, D.T)
+
+
 @pytest.mark.parametrize("gen,d", [("CKSWithRQSearchSpace", 6), ("CompositionalKernelSearchSpace", 8), ("CKSHighDimSearchSpace", 12)])
 def test_large_grammars(gen, d):
     """More base kernels / dim-wise columns than the benchmark grammars (B up to 24, F up to 36)."""
