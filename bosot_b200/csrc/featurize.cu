@@ -163,7 +163,7 @@ eval_build_kernel(uint8_t* __restrict__ blob, EvalLayout L, bosot_grammar g,
       meta.null_pos[b] = b < g.n_blocks ? pos_of_col[g.block_null_col[b]] : (int8_t)0;
       meta.n_states[b] = 0;
     }
-    meta.pad[0] = meta.pad[1] = meta.pad[2] = meta.pad[3] = 0;
+    meta.n_flat = 0;
     int* hdr = reinterpret_cast<int*>(blob);
     hdr[0] = E; hdr[1] = L.e_pad; hdr[2] = L.hash_cap; hdr[3] = L.n_slots; hdr[4] = n_dim_cols;
   }
@@ -235,6 +235,13 @@ eval_build_kernel(uint8_t* __restrict__ blob, EvalLayout L, bosot_grammar g,
     int ok = 1;
     for (int b = 0; b < g.n_blocks; ++b) ok = ok && (meta.n_states[b] <= kMaxStates);
     meta.use_states = ok;
+    uint32_t* flat = reinterpret_cast<uint32_t*>(blob + L.off_flat);
+    int k = 0;
+    for (int b = 0; b < g.n_blocks; ++b)
+      for (int s = 0; s < meta.n_states[b] && s < kMaxStates; ++s)
+        flat[k++] = (uint32_t)meta.bbeg[b] | ((uint32_t)meta.bbeg[b + 1] << 8) | ((uint32_t)(b * kMaxStates + s) << 16);
+    meta.n_flat = k;
+    for (; k < BOSOT_MAX_BLOCKS * kMaxStates; ++k) flat[k] = 0u;
   }
   __syncthreads();
   {

@@ -148,7 +148,7 @@ struct DimMeta {
   int8_t sym_pos[BOSOT_MAX_SYMBOLS];     // permuted position of a symbol's column, -1 = none
   int8_t null_pos[BOSOT_MAX_BLOCKS];     // permuted position of NULL_b
   uint8_t n_states[BOSOT_MAX_BLOCKS];    // distinct vectors per block (saturates at kMaxStates + 1)
-  uint8_t pad[4];
+  int32_t n_flat;                        // entries of the flat (block, state) list, see off_flat
 };
 static_assert(sizeof(DimMeta) == 128, "DimMeta is staged with one 128-byte bulk copy");
 
@@ -172,6 +172,8 @@ struct EvalLayout {
   size_t off_meta;     // DimMeta
   size_t off_stateP;   // double [BOSOT_MAX_DIM_COLS][kMaxStates]  value of permuted column j in state s of its block
   size_t off_sid8T;    // uint8  [BOSOT_MAX_BLOCKS][e_pad]  8 * (state of tree e in block b)
+  size_t off_flat;     // uint32 [BOSOT_MAX_BLOCKS * kMaxStates]  all (block, state) pairs in block order:
+                       //        first column | (last column + 1) << 8 | (block * kMaxStates + state) << 16
   size_t off_dimT;     // double [BOSOT_MAX_DIM_COLS][e_pad]  transposed dim-wise matrix, permuted column order
   size_t off_cursor;   // uint32 [n_slots]   build scratch
   size_t total;
@@ -201,6 +203,7 @@ __host__ __device__ inline EvalLayout eval_layout(int n_eval) {
   L.off_meta = o;      o = align16(o + sizeof(DimMeta));
   L.off_stateP = o;    o = align16(o + sizeof(double) * (size_t)BOSOT_MAX_DIM_COLS * kMaxStates);
   L.off_sid8T = o;     o = align16(o + (size_t)BOSOT_MAX_BLOCKS * L.e_pad);
+  L.off_flat = o;      o = align16(o + sizeof(uint32_t) * (size_t)BOSOT_MAX_BLOCKS * kMaxStates);
   L.off_dimT = o;      o = align16(o + sizeof(double) * (size_t)BOSOT_MAX_DIM_COLS * L.e_pad);
   L.off_cursor = o;    o = align16(o + sizeof(uint32_t) * (size_t)L.n_slots);
   L.total = o;

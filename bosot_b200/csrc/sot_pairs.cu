@@ -30,7 +30,7 @@
 
 namespace bosot {
 
-constexpr int kMaxPairWarps = 32;   // one persistent CTA of up to 32 warps per SM
+constexpr int kMaxPairWarps = 24;   // one persistent CTA of up to 24 warps per SM (80 registers per thread)
 constexpr int kScanThreads = 128;
 constexpr int kMaxR = 8;            // evaluated trees per lane per register tile (E <= 256 in one pass, else tiles of 256)
 
@@ -69,14 +69,15 @@ __host__ __device__ inline WarpLayout warp_layout(int e_pad, int n_dim_cols, int
 // The DIM_WISE section holds either the block-state tables (stateP + sid8T) or, when a block has more than
 // kMaxStates distinct vectors, the dense transposed matrix; it is sized for the larger of the two.
 struct StageLayout {
-  size_t off_meta, off_dim, off_sid, off_rsub, off_rpath, off_symT2, off_nn2, off_nn, off_nl, total;
-  uint32_t b_meta, b_state, b_sid, b_dimT, b_r, b_symT2, b_nn2, b_n;
+  size_t off_meta, off_dim, off_sid, off_flat, off_rsub, off_rpath, off_symT2, off_nn2, off_nn, off_nl, total;
+  uint32_t b_meta, b_state, b_sid, b_flat, b_dimT, b_r, b_symT2, b_nn2, b_n;
 };
 __host__ __device__ inline StageLayout stage_layout(int e_pad, int n_dim_cols, int n_symbols, int n_blocks) {
   StageLayout S;
   S.b_meta = (uint32_t)sizeof(DimMeta);
   S.b_state = (uint32_t)(sizeof(double) * (size_t)n_dim_cols * kMaxStates);
   S.b_sid = (uint32_t)((size_t)n_blocks * e_pad);
+  S.b_flat = (uint32_t)(sizeof(uint32_t) * (size_t)n_blocks * kMaxStates);
   S.b_dimT = (uint32_t)(sizeof(double) * (size_t)n_dim_cols * e_pad);
   S.b_r = (uint32_t)(sizeof(double) * (size_t)e_pad);
   S.b_symT2 = (uint32_t)(sizeof(uint32_t) * (size_t)n_symbols * (e_pad / 2));
@@ -84,8 +85,8 @@ __host__ __device__ inline StageLayout stage_layout(int e_pad, int n_dim_cols, i
   S.b_n = (uint32_t)e_pad;
   size_t o = 16;  // mbarrier
   S.off_meta = o;  o += S.b_meta;
-  S.off_dim = o;   S.off_sid = o + S.b_state;
-  o += (S.b_state + S.b_sid > S.b_dimT) ? (S.b_state + S.b_sid) : S.b_dimT;
+  S.off_dim = o;   S.off_sid = o + S.b_state;   S.off_flat = S.off_sid + S.b_sid;
+  o += (S.b_state + S.b_sid + S.b_flat > S.b_dimT) ? (S.b_state + S.b_sid + S.b_flat) : S.b_dimT;
   S.off_rsub = o;  o += S.b_r;
   S.off_rpath = o; o += S.b_r;
   S.off_symT2 = o; o += S.b_symT2;
@@ -209,11 +210,12 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   __syncthreads();
   if (threadIdx.x == 0) {
     const int states = __ldg(reinterpret_cast<const int*>(p.blob + p.L.off_meta));  // DimMeta::use_states
-    mbar_expect_tx(bar, S.b_meta + (states ? S.b_state + S.b_sid : S.b_dimT) + 2 * S.b_r + S.b_symT2 + S.b_nn2 + 2 * S.b_n);
+    mbar_expect_tx(bar, S.b_meta + (states ? S.b_state + S.b_sid + S.b_flat : S.b_dimT) + 2 * S.b_r + S.b_symT2 + S.b_nn2 + 2 * S.b_n);
     tma_bulk_g2s(smem + S.off_meta, p.blob + p.L.off_meta, S.b_meta, bar);
     if (states) {
       tma_bulk_g2s(smem + S.off_dim, p.blob + p.L.off_stateP, S.b_state, bar);
       tma_bulk_g2s(smem + S.off_sid, p.blob + p.L.off_sid8T, S.b_sid, bar);
+      tma_bulk_g2s(smem + S.off_flat, p.blob + p.L.off_flat, S.b_flat, bar);
     } else {
       tma_bulk_g2s(smem + S.off_dim, p.blob + p.L.off_dimT, S.b_dimT, bar);
     }
@@ -228,6 +230,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   const double* stateP = reinterpret_cast<const double*>(smem + S.off_dim);  // [n_pcols][kMaxStates]   (state mode)
   const double* dimT = stateP;                                               // [n_pcols][e_pad]        (dense mode)
   const uint8_t* sid8T = smem + S.off_sid;
+  const uint32_t* flat = reinterpret_cast<const uint32_t*>(smem + S.off_flat);  // (block, state) list
   const double* e_rsub = reinterpret_cast<const double*>(smem + S.off_rsub);
   const double* e_rpath = reinterpret_cast<const double*>(smem + S.off_rpath);
   const uint32_t* symT2 = reinterpret_cast<const uint32_t*>(smem + S.off_symT2);
@@ -249,6 +252,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   const uint32_t* post = reinterpret_cast<const uint32_t*>(p.blob + p.L.off_post);
   const int hash_cap = p.L.hash_cap;
   const size_t plane = (size_t)p.n_cand * p.ld;
+  const int ld_i = p.ld < (int64_t)e_pad ? (int)p.ld : e_pad;  // columns this kernel may touch
 
   // one lane-slice of a compact record: class id of operator node `lane`, symbol / path code of leaf `lane`
   struct Slice { unsigned long long id; uint32_t meta, sym, code; };
@@ -268,7 +272,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   if (t < p.n_cand) nxt = load_slice(t);
   mbar_wait(bar, 0);  // tables landed (the copy overlapped the first record load)
   const bool use_states = meta->use_states != 0;
-  const int n_pcols = meta->n_pcols;
+  const int n_flat = meta->n_flat;
 
   for (; t < p.n_cand; t += stride) {
     const Slice cur = nxt;
@@ -382,14 +386,17 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     walk(r_int, (uint32_t)__popc(m_id), (uint32_t)nn, 0);
     walk(r_pid, (uint32_t)__popc(m_pid), (uint32_t)nl, 16);
 
-    // block-state distance table: lane s holds state s of every block
+    // block-state distance table: one (block, state) pair per lane and round
     if (use_states) {
 #pragma unroll 1
-      for (int b = 0; b < g.n_blocks; ++b) {
+      for (int k = lane; k < n_flat; k += 32) {
+        const uint32_t dsc = flat[k];
+        const int j1 = (dsc >> 8) & 0xff, ts = dsc >> 16;
+        const double* sv = stateP + (ts & (kMaxStates - 1));
         double sum = 0.0;
 #pragma unroll 1
-        for (int j = meta->bbeg[b]; j < meta->bbeg[b + 1]; ++j) sum += fabs(avec[j] - stateP[j * kMaxStates + lane]);
-        tab[b * kMaxStates + lane] = sum;
+        for (int j = dsc & 0xff; j < j1; ++j) sum += fabs(avec[j] - sv[j * kMaxStates]);
+        tab[ts] = sum;
       }
     }
     __syncwarp();
@@ -487,12 +494,13 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
         if (p.K) {
           exp_nonpos_group<kG>(x);
 #pragma unroll
+          for (int i = 0; i < kG; ++i)  // pin the results here: otherwise every chain is sunk into its own guarded store
+            if (r0 + i < R) asm volatile("" : "+d"(x[i]));
+#pragma unroll
           for (int i = 0; i < kG; ++i) {
             const int r = r0 + i, e = eb + 32 * r;
-            if (r < R) {
-              if (e < E) p.K[row + e] = p.variance * x[i];
-              else if (e < p.ld) p.K[row + e] = 0.0;  // padding columns of the Gram row stay finite (the posterior kernel may read them)
-            }
+            // padding columns of the Gram row stay finite (the posterior kernel may read them)
+            if (r < R && e < ld_i) p.K[row + e] = e < E ? p.variance * x[i] : 0.0;
           }
         }
       }
