@@ -402,7 +402,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     __syncwarp();
 
     // ---- phase C: register tiles of R evaluated trees per lane (tree e = e0 + lane + 32 r)
-    const double rTa_sub = c_recip[nn], rTa_path = c_recip[nl];
+    const double rTa2_sub = 2.0 * c_recip[nn], rTa2_path = 2.0 * c_recip[nl];
     for (int e0 = 0; e0 < E; e0 += 32 * R) {
       const int eb = e0 + lane;  // e_pad is a whole number of tiles: eb + 32 r < e_pad, padded arrays stay in bounds
       uint32_t msub2[RP];
@@ -471,11 +471,10 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
             const uint32_t a = accp[32 * r];
             const uint32_t m_sub = ((msub2[r >> 1] >> (16 * (r & 1))) & 0xffffu) + (a & 0xffffu), m_path = a >> 16;
             const uint32_t tb_sub = nnp[32 * r], tb_path = nlp[32 * r];
-            // 2 - 2*M/(Ta*Tb); exactly 0 when the histograms coincide; (1/Ta)*(1/Tb) first keeps D(a,b) == D(b,a) bitwise
-            double d_sub = fma(-2.0, u32_to_f64(m_sub) * (rTa_sub * rsp[32 * r]), 2.0);
-            double d_path = fma(-2.0, u32_to_f64(m_path) * (rTa_path * rpp[32 * r]), 2.0);
-            d_sub = (m_sub == (uint32_t)nn * tb_sub) ? 0.0 : d_sub;
-            d_path = (m_path == (uint32_t)nl * tb_path) ? 0.0 : d_path;
+            // L1 = 2 - 2 M / (Ta Tb) = 2 (Ta Tb - M) / (Ta Tb) with the integer difference formed first: exactly 0
+            // when the histograms coincide (like the reference), and (1/Ta)(1/Tb) first keeps D(a,b) == D(b,a) bitwise
+            const double d_sub = u32_to_f64((uint32_t)nn * tb_sub - m_sub) * (rTa2_sub * rsp[32 * r]);
+            const double d_path = u32_to_f64((uint32_t)nl * tb_path - m_path) * (rTa2_path * rpp[32 * r]);
             // sum_f w_f * D_f in feature_type_list order (kernel_kernel_grammar_tree.py:159-161)
             const double d = __dadd_rn(__dadd_rn(__dmul_rn(p.w_dim, ddim[r]), __dmul_rn(p.w_path, d_path)),
                                        __dmul_rn(p.w_sub, d_sub));
