@@ -179,13 +179,15 @@ posterior_kernel(PostParams p) {
 }
 
 // ---- warp-specialised variant -----------------------------------------------------------------
-// One persistent CTA per SM: warp 0 streams K* tiles (TC candidates) into a 2-stage shared-memory ring
-// with TMA bulk row copies completing on "full" mbarriers; the consumer warps pull (tile, unit) work
-// items from ONE shared queue -- units of a tile = its 16-row blocks of L^-1, largest first, then the
-// mean dot products -- so nobody ever waits at a CTA-wide barrier: the warp that completes the last
-// unit of a tile runs that tile's epilogue and hands the stage back through the "empty" mbarrier.
+// One persistent CTA of 8 warps per SM (2 per scheduler: room for ~190 registers per thread).  K* tiles (TC
+// candidates) live in a 2-stage shared-memory ring filled by TMA bulk row copies completing on "full" mbarriers.
+// The warps pull (tile, unit) work items from ONE shared queue -- units of a tile = its 16-row blocks of L^-1,
+// largest first, then the mean dot products -- so nobody ever waits at a CTA-wide barrier.  The warp that
+// completes the last unit of a tile immediately issues the copies of the tile after next into the stage it just
+// freed (no producer warp, no "empty" barrier) and runs the tile's epilogue behind that copy; units of the later
+// tile check a flag before they overwrite the partial sums / means the epilogue is still reading.
 constexpr int kWsConsumers = 8;
-constexpr int kWsThreads = (kWsConsumers + 1) * 32;
+constexpr int kWsThreads = kWsConsumers * 32;
 
 __device__ __forceinline__ uint32_t ws_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ws_mbar_init(uint64_t* bar, uint32_t count) {
@@ -193,9 +195,6 @@ __device__ __forceinline__ void ws_mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void ws_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ws_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void ws_mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ws_smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void ws_tma_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -220,7 +219,7 @@ __host__ __device__ inline WsLayout ws_layout(int E) {
   WsLayout W;
   W.tld = post_tile_ld(E);
   W.n_blk = (E + kRowBlk - 1) / kRowBlk;
-  size_t o = 64;  // full[2], empty[2], next_work, done[2]
+  size_t o = 64;  // full[2], next_work, done[2], epi[2]
   W.off_ks = o;   o += sizeof(double) * 2 * (size_t)TC * W.tld;
   W.off_red = o;  o += sizeof(double) * 2 * (size_t)W.n_blk * TC;
   W.off_mus = o;  o += sizeof(double) * 2 * TC;
@@ -238,9 +237,9 @@ posterior_ws_kernel(PostParams p) {
   const int tld = W.tld, n_blk = W.n_blk, n_units = n_blk + 1;
   const int ks_max = (E + 3) >> 2;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* empty = full + 2;
   int* next_work = reinterpret_cast<int*>(smem + 32);
   int* done = next_work + 1;  // [2]
+  volatile int* epi = done + 2;  // [2] set while the epilogue of the tile that used the stage before still reads its sums / means
   double* Ks = reinterpret_cast<double*>(smem + W.off_ks);
   double* red = reinterpret_cast<double*>(smem + W.off_red);
   double* mus = reinterpret_cast<double*>(smem + W.off_mus);
@@ -252,29 +251,27 @@ posterior_ws_kernel(PostParams p) {
 
   if (threadIdx.x == 0) {
     ws_mbar_init(&full[0], 1); ws_mbar_init(&full[1], 1);
-    ws_mbar_init(&empty[0], 1); ws_mbar_init(&empty[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    *next_work = 0; done[0] = 0; done[1] = 0;
+    *next_work = 0; done[0] = 0; done[1] = 0; epi[0] = 0; epi[1] = 0;
   }
   for (int x = threadIdx.x; x < (int)((W.total - W.off_ks) / sizeof(double)); x += kWsThreads) Ks[x] = 0.0;  // everything finite
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");             // generic-proxy zeros before async-proxy writes
   __syncthreads();
 
-  if (warp == kWsConsumers) {
-    // ---------------- producer: one lane issues the row copies of every tile of this CTA
-    if (lane == 0) {
-      for (int i = 0; i < n_my; ++i) {
-        const int s = i & 1;
-        if (i >= 2) ws_mbar_wait(&empty[s], ((i >> 1) - 1) & 1);
-        const int64_t c0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * TC;
-        const int rows = (int)min((int64_t)TC, p.n_cand - c0);
-        const uint32_t row_bytes = (uint32_t)((E + 1) & ~1) * 8u;  // whole 16-byte units; for odd E one (finite) padding column comes along
-        ws_mbar_expect_tx(&full[s], (uint32_t)rows * row_bytes);
-        double* dst = Ks + (size_t)s * TC * tld;
-        for (int c = 0; c < rows; ++c) ws_tma_g2s(dst + (size_t)c * tld, p.Kstar + (c0 + c) * p.ld, row_bytes, &full[s]);
-      }
-    }
-    return;
+  // one warp issues the TMA row copies of this CTA's tile number i into stage i & 1 (every lane its share of the rows)
+  const uint32_t row_bytes = (uint32_t)((E + 1) & ~1) * 8u;  // whole 16-byte units; for odd E one (finite) padding column comes along
+  auto issue_tile = [&](int i) {
+    const int s = i & 1;
+    const int64_t c0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * TC;
+    const int rows = (int)min((int64_t)TC, p.n_cand - c0);
+    if (lane == 0) ws_mbar_expect_tx(&full[s], (uint32_t)rows * row_bytes);
+    __syncwarp();
+    double* dst = Ks + (size_t)s * TC * tld;
+    for (int c = lane; c < rows; c += 32) ws_tma_g2s(dst + (size_t)c * tld, p.Kstar + (c0 + c) * p.ld, row_bytes, &full[s]);
+  };
+  if (warp == 0) {
+    if (n_my > 0) issue_tile(0);
+    if (n_my > 1) issue_tile(1);
   }
 
   // ---------------- consumers
@@ -308,14 +305,14 @@ posterior_ws_kernel(PostParams p) {
       const double* a_lo = a_up + (size_t)KS * 32;
       const double* bp = Kt + g * tld + t;
       const int nks_pad = (nks + kPD - 1) & ~(kPD - 1);
-      double ra_up[kPD], ra_lo[kPD], b_cur[NB], b_nxt[NB];
+      double ra_up[kPD], ra_lo[kPD], bf[2][NB];  // B fragments ping-pong between two register sets (kPD is even)
 #pragma unroll
       for (int u = 0; u < kPD; ++u) {
         ra_up[u] = __ldg(a_up + 32 * u);
         ra_lo[u] = lower_live ? __ldg(a_lo + 32 * u) : 0.0;
       }
 #pragma unroll
-      for (int nb = 0; nb < NB; ++nb) b_cur[nb] = bp[(size_t)nb * 8 * tld];
+      for (int nb = 0; nb < NB; ++nb) bf[0][nb] = bp[(size_t)nb * 8 * tld];
       for (int ks0 = 0; ks0 < nks_pad; ks0 += kPD) {
 #pragma unroll
         for (int u = 0; u < kPD; ++u) {
@@ -325,38 +322,60 @@ posterior_ws_kernel(PostParams p) {
             ra_up[u] = __ldg(a_up + 32 * (ks + kPD));
             ra_lo[u] = lower_live ? __ldg(a_lo + 32 * (ks + kPD)) : 0.0;
           }
-          if (ks + 1 < nks_pad) {
+          // next step's B fragments (after the last step this reads a few finite doubles past the row: never used)
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb) b_nxt[nb] = bp[(size_t)nb * 8 * tld + 4 * (ks + 1)];
-          }
+          for (int nb = 0; nb < NB; ++nb) bf[(u + 1) & 1][nb] = bp[(size_t)nb * 8 * tld + 4 * (ks + 1)];
           if (ks < nks_up) {
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb) dmma8x8x4(up[nb][0], up[nb][1], au, b_cur[nb]);
+            for (int nb = 0; nb < NB; ++nb) dmma8x8x4(up[nb][0], up[nb][1], au, bf[u & 1][nb]);
           }
           if (lower_live) {
 #pragma unroll
-            for (int nb = 0; nb < NB; ++nb) dmma8x8x4(lo[nb][0], lo[nb][1], al, b_cur[nb]);
+            for (int nb = 0; nb < NB; ++nb) dmma8x8x4(lo[nb][0], lo[nb][1], al, bf[u & 1][nb]);
           }
-#pragma unroll
-          for (int nb = 0; nb < NB; ++nb) b_cur[nb] = b_nxt[nb];
         }
       }
+      while (epi[s]) {}  // the previous tile's epilogue may still be reading this stage's sums
+      // Column sums of squares over the 16 rows: own rows first, then across the 8 row groups (lane bits 2..4) by a
+      // halving butterfly -- at every level a lane keeps one half of its values and receives the partner's half,
+      // so 2 NB values per lane shrink to 2 NB / 8 fully reduced ones with 2 NB - 2 NB / 8 exchanges.
+      double v[2 * NB];
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
-        double s0 = fma(up[nb][0], up[nb][0], lo[nb][0] * lo[nb][0]);
-        double s1 = fma(up[nb][1], up[nb][1], lo[nb][1] * lo[nb][1]);
+        v[2 * nb] = fma(up[nb][0], up[nb][0], lo[nb][0] * lo[nb][0]);
+        v[2 * nb + 1] = fma(up[nb][1], up[nb][1], lo[nb][1] * lo[nb][1]);
+      }
+      int n = 2 * NB, base = 0;
+      bool writer = true;
 #pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      for (int lvl = 0; lvl < 3; ++lvl) {
+        const int o = 4 << lvl;
+        const bool hi = (lane & o) != 0;
+        if (n >= 2) {
+          n >>= 1;
+#pragma unroll
+          for (int j = 0; j < NB; ++j) {
+            if (j < n) {
+              const double send = hi ? v[j] : v[j + n];
+              const double keep = hi ? v[j + n] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+            }
+          }
+          base += hi ? n : 0;
+        } else {
+          v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+          writer = writer && !hi;
         }
-        if (g == 0) {
-          red_s[m * TC + nb * 8 + 2 * t] = s0;
-          red_s[m * TC + nb * 8 + 2 * t + 1] = s1;
-        }
+      }
+      // the n values left on this lane are original indices base .. base + n - 1 (index = 2 nb + column parity)
+      if (n == 2) {
+        *reinterpret_cast<double2*>(&red_s[m * TC + (base >> 1) * 8 + 2 * t]) = make_double2(v[0], v[1]);
+      } else if (writer) {
+        red_s[m * TC + (base >> 1) * 8 + 2 * t + (base & 1)] = v[0];
       }
     } else {
       // mean unit: K* . beta for the TC candidates of the tile (same 4-way split per candidate as the generic kernel)
+      while (epi[s]) {}
       for (int c = lane >> 2; c < TC; c += 8) {
         const int q = lane & 3;
         double sacc = 0.0;
@@ -374,6 +393,12 @@ posterior_ws_kernel(PostParams p) {
     d = __shfl_sync(0xffffffffu, d, 0);
     if (d == n_units - 1) {
       __threadfence_block();
+      // the K* tile of this stage is dead: refill it NOW (tile after next) and run the epilogue behind the copy; units
+      // of that later tile wait on epi[s] before they overwrite the sums / means the epilogue is reading
+      if (lane == 0) { epi[s] = 1; done[s] = 0; }
+      __threadfence_block();
+      __syncwarp();
+      if (i + 2 < n_my) issue_tile(i + 2);
       const int64_t c0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * TC;
       const int in_tile = (int)min((int64_t)TC, p.n_cand - c0);
       for (int c = lane; c < in_tile; c += 32) {
@@ -399,11 +424,9 @@ posterior_ws_kernel(PostParams p) {
         }
       }
       __syncwarp();
-      if (lane == 0) {
-        done[s] = 0;
-        __threadfence_block();
-        ws_mbar_arrive(&empty[s]);
-      }
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) epi[s] = 0;
     }
   }
 }
