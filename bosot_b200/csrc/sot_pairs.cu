@@ -30,7 +30,7 @@
 
 namespace bosot {
 
-constexpr int kMaxPairWarps = 24;   // one persistent CTA of up to 24 warps per SM (80 registers per thread)
+constexpr int kMaxPairWarps = 28;   // one persistent CTA of up to 28 warps per SM (72 registers per thread; measured: 20 / 24 / 28 / 32 warps = 2.68 / 2.52 / 2.43 / 2.49 ms)
 constexpr int kScanThreads = 128;
 constexpr int kMaxR = 8;            // evaluated trees per lane per register tile (E <= 256 in one pass, else tiles of 256)
 
