@@ -141,6 +141,9 @@ def main() -> None:
     ap.add_argument("--pool", type=int, default=POOL)
     ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the cpu_baseline sample (0 = 100 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: 'fused' = the posterior kernel stores EI into every GPU's vector over NVLink peer memory + one "
+                         "symmetric-memory barrier; 'nccl' = all_gather_into_tensor after the kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -196,7 +199,24 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    scatter = None
+    if world > 1 and args.collective == "fused":
+        from bosot_b200.distributed import PeerScatter
+
+        try:
+            scatter = PeerScatter(pool, dev)
+            assert scatter.bounds == (lo, hi)
+            ei_full = scatter.values
+        except Exception as exc:  # symmetric memory unavailable on this box: say so and use NCCL
+            print("bench: symmetric memory unavailable (%s: %s); falling back to the NCCL all-gather" % (type(exc).__name__, exc),
+                  file=sys.stderr)
+            scatter = None
+
     def step_device():
+        if scatter is not None:
+            eng.acquire_device(d_ca, out=(mu, sigma, ei_local), scatter=scatter.scatter_args())
+            scatter.barrier()
+            return
         eng.acquire_device(d_ca, out=(mu, sigma, ei_local))
         if world > 1:
             dist.all_gather_into_tensor(ei_full, ei_local)
@@ -208,10 +228,14 @@ def main() -> None:
     d_stage = torch.empty_like(d_ca)
 
     def step_e2e_multi():
-        # N > 1: pinned H2D of the shard, kernels, all-gather on the device, pinned D2H of the full EI vector
+        # N > 1: pinned H2D of the shard, kernels, exchange of the EI shards on the device, pinned D2H of the full EI vector
         d_stage.copy_(h_ca, non_blocking=True)
-        eng.acquire_device(d_stage, out=(mu, sigma, ei_local))
-        dist.all_gather_into_tensor(ei_full, ei_local)
+        if scatter is not None:
+            eng.acquire_device(d_stage, out=(mu, sigma, ei_local), scatter=scatter.scatter_args())
+            scatter.barrier()
+        else:
+            eng.acquire_device(d_stage, out=(mu, sigma, ei_local))
+            dist.all_gather_into_tensor(ei_full, ei_local)
         h_ei.copy_(ei_full, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
 
@@ -388,14 +412,16 @@ def main() -> None:
             metric="sot_ot_pairs_per_sec", value=value, unit="pairs/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=ms_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f64", data="synthetic",
             config=dict(workload="c5_stress_1M_x_200", pool=pool, n_eval=N_EVAL, generator=GEN, input_dimension=DIM, hyper="H1",
-                        sharding="candidate row blocks, %d per GPU" % n_local, collective="all_gather(EI) x1" if world > 1 else "none",
+                        sharding="candidate row blocks, %d per GPU" % n_local, collective=("none" if world == 1 else
+                                    "fused: posterior kernel stores EI into every GPU's vector (NVLink peer memory) + 1 symmetric-memory barrier"
+                                    if scatter is not None else "all_gather(EI) x1"),
                         l2="flushed between timed steps (512 MB memset, untimed); working set also exceeds L2"),
             ei_candidates_per_sec=pool / (ms_step * 1e-3),
             clocks=clocks.summary(),
             e2e=dict(value=e2e_value, unit="pairs/s", ms_per_step=ms_e2e, ei_candidates_per_sec=pool / (ms_e2e * 1e-3),
                      h2d_bytes_per_step=pool * 64, d2h_bytes_per_step=pool * 8 * world,
                      api="AcquisitionEngine.acquire_host (C-ABI bosot_acquire_host)" if world == 1 else
-                         "pinned H2D + AcquisitionEngine.acquire_device + all_gather + pinned D2H"),
+                         "pinned H2D + AcquisitionEngine.acquire_device + EI exchange (config.collective) + pinned D2H"),
             gpu_launches=launches * world,
             roofline=roofline,
             cpu_baseline=cpu,

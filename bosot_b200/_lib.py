@@ -90,6 +90,16 @@ SIGNATURES = {
         [_P, C.c_int64, _G, _P, C.c_int, _D3, C.c_double, C.c_double, _P, C.c_int, _P, C.c_double, C.c_int, _P, C.c_double, C.c_double,
          _P, C.c_size_t, _P, _P, _P, _P],
     ),
+    "bosot_posterior_acq_scatter": (
+        C.c_int,
+        [_P, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, _P, C.c_double, C.c_double, C.c_int, _P, C.c_double, C.c_double, _P, _P, _P,
+         _P, C.c_int, C.c_int64, _P],
+    ),
+    "bosot_acquire_device_scatter": (
+        C.c_int,
+        [_P, C.c_int64, _G, _P, C.c_int, _D3, C.c_double, C.c_double, _P, C.c_int, _P, C.c_double, C.c_int, _P, C.c_double, C.c_double,
+         _P, C.c_size_t, _P, _P, _P, _P, C.c_int, C.c_int64, _P],
+    ),
     "bosot_neighbours": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P, _P]),
     "bosot_gp_fit_max_eval": (C.c_int, []),
     "bosot_gp_nll_grad": (C.c_int, [_P, C.c_int, C.c_int64, _P, _D3, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P]),

@@ -48,7 +48,8 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
 size_t pairs_scratch_bytes(int64_t n_cand);
 int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval, const double* d_Linv, int ldl,
                      const double* d_beta, double mean_c, double variance, int acq_kind, const double* d_current_max,
-                     double xi, double ucb_beta, double* d_mu, double* d_sigma, double* d_acq, cudaStream_t stream);
+                     double xi, double ucb_beta, double* d_mu, double* d_sigma, double* d_acq, cudaStream_t stream,
+                     double* const* d_peers = nullptr, int n_peers = 0, int64_t peer_off = 0);
 
 // work buffer of the composed calls:  K*[n_cand][ld] | trees[n_cand][64] | mu | sigma | acq | status | scan records
 struct WorkLayout {
@@ -86,6 +87,17 @@ extern "C" int bosot_posterior_acq(const double* d_Kstar, int64_t n_cand, int64_
                           xi, ucb_beta, d_mu, d_sigma, d_acq, (cudaStream_t)stream);
 }
 
+extern "C" int bosot_posterior_acq_scatter(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval,
+                                           const double* d_Linv, int ldl, const double* d_beta, double mean_c, double variance,
+                                           int acq_kind, const double* d_current_max, double xi, double ucb_beta,
+                                           double* d_mu, double* d_sigma, double* d_acq,
+                                           const void* d_peer_ptrs, int n_peers, int64_t peer_offset, void* stream) {
+  if (!d_peer_ptrs) return set_error(BOSOT_EINVAL, "bosot_posterior_acq_scatter: null peer pointer table");
+  return launch_posterior(d_Kstar, n_cand, ld, n_eval, d_Linv, ldl, d_beta, mean_c, variance, acq_kind, d_current_max,
+                          xi, ucb_beta, d_mu, d_sigma, d_acq, (cudaStream_t)stream,
+                          static_cast<double* const*>(d_peer_ptrs), n_peers, peer_offset);
+}
+
 extern "C" size_t bosot_acquire_work_bytes(int64_t n_cand, int n_eval) {
   if (n_cand < 0 || n_eval < 1 || n_eval > BOSOT_MAX_EVAL) return 0;
   return work_layout(n_cand, n_eval).total;
@@ -110,6 +122,28 @@ extern "C" int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, cons
                             nullptr, W.ld, status, w + W.off_recs, pairs_scratch_bytes(n_cand), st)) return rc;
   return launch_posterior(K, n_cand, W.ld, n_eval, d_Linv, ldl, d_beta, mean_c, variance, acq_kind, d_current_max, xi,
                           ucb_beta, d_mu, d_sigma, d_acq, st);
+}
+
+extern "C" int bosot_acquire_device_scatter(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,
+                                            const void* d_eval_blob, int n_eval, const double weights[3],
+                                            double variance, double lengthscale,
+                                            const double* d_Linv, int ldl, const double* d_beta, double mean_c,
+                                            int acq_kind, const double* d_current_max, double xi, double ucb_beta,
+                                            void* d_work, size_t work_bytes,
+                                            double* d_mu, double* d_sigma, double* d_acq,
+                                            const void* d_peer_ptrs, int n_peers, int64_t peer_offset, void* stream) {
+  if (!d_work || !d_peer_ptrs) return set_error(BOSOT_EINVAL, "bosot_acquire_device_scatter: null argument");
+  if (n_cand < 0 || n_eval < 1 || n_eval > BOSOT_MAX_EVAL) return set_error(BOSOT_EINVAL, "bosot_acquire_device_scatter: bad sizes");
+  const WorkLayout W = work_layout(n_cand, n_eval);
+  if (work_bytes < W.total) return set_error(BOSOT_EINVAL, "bosot_acquire_device_scatter: work buffer too small");
+  uint8_t* w = static_cast<uint8_t*>(d_work);
+  double* K = reinterpret_cast<double*>(w + W.off_K);
+  int32_t* status = reinterpret_cast<int32_t*>(w + W.off_status);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = launch_pairs(d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale, K, nullptr,
+                            nullptr, W.ld, status, w + W.off_recs, pairs_scratch_bytes(n_cand), st)) return rc;
+  return launch_posterior(K, n_cand, W.ld, n_eval, d_Linv, ldl, d_beta, mean_c, variance, acq_kind, d_current_max, xi,
+                          ucb_beta, d_mu, d_sigma, d_acq, st, static_cast<double* const*>(d_peer_ptrs), n_peers, peer_offset);
 }
 
 // helper streams / events for the pipelined host entry point (created lazily, one set per device, never destroyed)

@@ -44,6 +44,11 @@ struct PostParams {
   double* mu;
   double* sigma;
   double* acq;
+  // optional scatter of the acquisition value into the row-sharded result vector of every GPU of the node
+  // (peer memory over NVLink / NVSwitch): peers[r][peer_off + candidate] = acq, r = 0 .. n_peers-1
+  double* const* peers;
+  int n_peers;
+  int64_t peer_off;
 };
 
 // K* tile row stride (doubles): == 4 or 12 (mod 16) so that the B-fragment read
@@ -173,6 +178,10 @@ posterior_kernel(PostParams p) {
           a = mval;
         }
         p.acq[c0 + c] = a;
+        if (p.peers) {
+#pragma unroll 1
+          for (int r = 0; r < p.n_peers; ++r) p.peers[r][p.peer_off + c0 + c] = a;
+        }
       }
     }
   }
@@ -421,6 +430,10 @@ posterior_ws_kernel(PostParams p) {
             a = mval;
           }
           p.acq[c0 + c] = a;
+          if (p.peers) {
+#pragma unroll 1
+            for (int r = 0; r < p.n_peers; ++r) p.peers[r][p.peer_off + c0 + c] = a;
+          }
         }
       }
       __syncwarp();
@@ -554,12 +567,15 @@ __global__ void fp64_mixed_probe_kernel(double* out, int iters) {
 
 int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval, const double* d_Linv, int ldl,
                      const double* d_beta, double mean_c, double variance, int acq_kind, const double* d_current_max,
-                     double xi, double ucb_beta, double* d_mu, double* d_sigma, double* d_acq, cudaStream_t stream) {
+                     double xi, double ucb_beta, double* d_mu, double* d_sigma, double* d_acq, cudaStream_t stream,
+                     double* const* d_peers, int n_peers, int64_t peer_off) {
   if (!d_Kstar || !d_Linv || !d_beta || n_cand < 0) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: null argument");
   if (n_eval < 1 || n_eval > BOSOT_MAX_EVAL || ld < n_eval) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: bad n_eval / ld");
   if (ldl < n_eval || (ldl % kRowBlk) != 0)
     return set_error(BOSOT_EINVAL, "bosot_posterior_acq: Linv must be [ldl][ldl] with ldl a multiple of 16 and >= n_eval");
   if (acq_kind == BOSOT_ACQ_EI && d_acq && !d_current_max) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: EI needs current_max");
+  if (d_peers && (!d_acq || n_peers < 1 || n_peers > 64 || peer_off < 0))
+    return set_error(BOSOT_EINVAL, "bosot_posterior_acq: the peer scatter needs d_acq, 1 <= n_peers <= 64 and a non-negative offset");
   if (n_cand == 0) return BOSOT_OK;
 
   PostParams p;
@@ -567,6 +583,7 @@ int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_ev
   p.Linv = d_Linv; p.beta = d_beta; p.mean_c = mean_c; p.variance = variance;
   p.acq_kind = acq_kind; p.cur_max = d_current_max; p.xi = xi; p.sqrt_ucb_beta = sqrt(ucb_beta);
   p.mu = d_mu; p.sigma = d_sigma; p.acq = d_acq;
+  p.peers = d_peers; p.n_peers = d_peers ? n_peers : 0; p.peer_off = peer_off;
 
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);

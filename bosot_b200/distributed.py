@@ -59,6 +59,31 @@ class ShardedAcquisition:
         return torch.cat(parts)
 
 
+class PeerScatter:
+    """Result vector of a row-sharded pool, replicated on every GPU of the node WITHOUT a collective after the
+    kernel: a symmetric-memory allocation (every rank's buffer is peer-mapped on all others over NVLink / NVSwitch)
+    that the posterior kernel's epilogue writes directly (C-ABI ``bosot_acquire_device_scatter``), followed by one
+    symmetric-memory barrier.  GPU + NCCL process group only; ``ShardedAcquisition`` is the portable path."""
+
+    def __init__(self, n: int, device: torch.device, group: Optional[dist.ProcessGroup] = None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.n = int(n)
+        self.values = symm_mem.empty(self.n, dtype=torch.float64, device=device)  # this rank's copy of the full vector
+        self.handle = symm_mem.rendezvous(self.values, self.group)
+        self.bounds = shard_bounds(self.n, self.world, self.rank)
+
+    def scatter_args(self) -> Tuple[int, int, int]:
+        """``scatter=`` argument of ``AcquisitionEngine.acquire_device`` for this rank's shard."""
+        return int(self.handle.buffer_ptrs_dev), self.world, self.bounds[0]
+
+    def barrier(self) -> None:
+        """All ranks' kernels have stored their shards everywhere once this returns on the current stream."""
+        self.handle.barrier()
+
+
 def argmax_pairs(values_local: torch.Tensor, offset: int, group: Optional[dist.ProcessGroup] = None) -> Tuple[float, int]:
     """Cheaper exchange for argmax-only consumers: all-gather of one (value, global index) pair per rank."""
     if values_local.numel():

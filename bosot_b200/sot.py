@@ -296,21 +296,30 @@ class AcquisitionEngine:
             self._work = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._work
 
-    def acquire_device(self, trees: torch.Tensor, out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
-        """Candidates already resident in HBM -> (mu, sigma, acq) device tensors."""
+    def acquire_device(self, trees: torch.Tensor, out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None,
+                       scatter: Optional[Tuple[int, int, int]] = None):
+        """Candidates already resident in HBM -> (mu, sigma, acq) device tensors.
+
+        ``scatter = (peer_ptrs_dev, n_peers, row_offset)``: the posterior kernel additionally stores every acquisition
+        value into the peer-mapped result vectors of all GPUs of the node at ``row_offset + i`` (C-ABI
+        ``bosot_acquire_device_scatter``; see ``bosot_b200.distributed.PeerScatter``)."""
         _need_cuda(trees, "candidate trees")
         n = trees.shape[0]
         if out is None:
             out = tuple(torch.empty(n, dtype=torch.float64, device=self.device) for _ in range(3))
         mu, sigma, acq = out
         w = self._workspace(n)
-        with torch.cuda.device(self.device):
-            rc = _lib.load().bosot_acquire_device(
-                trees.data_ptr(), n, C.byref(self.grammar.c_struct), self.state.blob.data_ptr(), self.n_eval, self._wdbl,
+        lib = _lib.load()
+        head = (trees.data_ptr(), n, C.byref(self.grammar.c_struct), self.state.blob.data_ptr(), self.n_eval, self._wdbl,
                 self.variance, self.lengthscale, self.Linv.data_ptr(), self.Linv.shape[1], self.beta.data_ptr(), self.mean_c,
                 self.acq_kind, self.current_max.data_ptr(), self.xi, self.ucb_beta, w.data_ptr(), w.numel(),
-                mu.data_ptr(), sigma.data_ptr(), acq.data_ptr(), _stream(self.device),
-            )
+                mu.data_ptr(), sigma.data_ptr(), acq.data_ptr())
+        with torch.cuda.device(self.device):
+            if scatter is None:
+                rc = lib.bosot_acquire_device(*head, _stream(self.device))
+            else:
+                ptrs, n_peers, offset = scatter
+                rc = lib.bosot_acquire_device_scatter(*head, ptrs, int(n_peers), int(offset), _stream(self.device))
         _lib.check(rc, "acquire_device")
         return mu, sigma, acq
 

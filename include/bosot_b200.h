@@ -200,6 +200,30 @@ int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, const bosot_gra
                          void* d_work, size_t work_bytes,
                          double* d_mu, double* d_sigma, double* d_acq, void* stream);
 
+/* ---- row-sharded pools: posterior + acquisition fused with the exchange of the result ----
+ * The reference has no multi-process path; here the candidate pool is split into row blocks over the GPUs of one
+ * node and every GPU needs the whole acquisition vector (the evolutionary optimiser selects on it,
+ * bosot/bayesian_optimization/evolutionary_optimizer_objects.py:57-71).  Instead of an all-gather after the kernel,
+ * the epilogue of the posterior kernel stores every acquisition value straight into the result vector of EVERY GPU:
+ *     peer[r][peer_offset + c] = acq[c]     for r = 0 .. n_peers-1 (the own buffer included), c = 0 .. n_cand-1
+ * d_peer_ptrs: device array of n_peers (<= 64) device pointers to fp64 buffers that are peer-mapped on this GPU
+ * (NVLink / NVSwitch P2P, e.g. a torch symmetric-memory allocation); peer_offset = first global row of this shard.
+ * d_acq (the local copy) is still written and must not be NULL.  The caller orders the buffers with a cross-GPU
+ * barrier after the call (symmetric-memory barrier) before any rank reads its vector. */
+int bosot_posterior_acq_scatter(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval,
+                                const double* d_LinvF, int ldl, const double* d_beta, double mean_c, double variance,
+                                int acq_kind, const double* d_current_max, double xi, double ucb_beta,
+                                double* d_mu, double* d_sigma, double* d_acq,
+                                const void* d_peer_ptrs, int n_peers, int64_t peer_offset, void* stream);
+int bosot_acquire_device_scatter(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,
+                                 const void* d_eval_blob, int n_eval, const double weights[3],
+                                 double variance, double lengthscale,
+                                 const double* d_LinvF, int ldl, const double* d_beta, double mean_c,
+                                 int acq_kind, const double* d_current_max, double xi, double ucb_beta,
+                                 void* d_work, size_t work_bytes,
+                                 double* d_mu, double* d_sigma, double* d_acq,
+                                 const void* d_peer_ptrs, int n_peers, int64_t peer_offset, void* stream);
+
 /* ---- hyper-parameter fit of the GP over kernels ----------------------------------
  * One launch = one evaluation of GPR's training loss (negative log marginal likelihood; reference
  * bosot/models/gp_model.py:195-199) and its analytic gradient, for K = variance*exp(-D/ls^2) + noise*I,
