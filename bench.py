@@ -392,6 +392,21 @@ def main() -> None:
                   posterior_frac_of_dmma_peak=post_flops / (ms_post * 1e-3) / 1e12 / dmma_tflops),
     )
 
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and c4:
+        # the same CPU port at the headline shape (north_star: >= 100x the reference's CPU kernel-kernel + EI throughput
+        # for a 10k-candidate x 50-evaluated matrix): bounded sample, all host cores, doubles as a parity check
+        from oracle import cpu_baseline
+
+        cores4 = os.cpu_count() or 1
+        sample4 = min(C4_POOL, 200 * cores4)
+        r4 = cpu_baseline.run(ev4, ca4[:sample4], y4, H1, GEN, DIM, chunk=100, n_procs=cores4)
+        ok4 = bool(np.allclose(o4[2][:sample4].cpu().numpy(), r4["acq"], rtol=1e-6, atol=1e-12))
+        c4["cpu_port"] = dict(pairs_per_s=r4["pairs_per_s"], ei_candidates_per_s=r4["cand_per_s"], cores=r4["cores"],
+                              sample="first %d candidates x %d evaluated in %.1f s: %d worker processes, calls of 100 candidates; "
+                                     "K_diag taken as variance" % (sample4, C4_EVAL, r4["seconds"], r4["cores"]),
+                              gpu_matches_cpu_on_sample=ok4)
+        c4["e2e_speedup_vs_cpu_port"] = c4["e2e_ei_candidates_per_s"] / r4["cand_per_s"]
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_baseline
