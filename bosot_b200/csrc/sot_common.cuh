@@ -84,24 +84,26 @@ __device__ __forceinline__ int scan_tree(uint8_t* rec, int n_symbols) {
   if (n < 1 || n > kMaxNodes || !(n & 1)) {
     status = BOSOT_TREE_BAD_LENGTH;
   } else {
+    // Pass 1, branch-free per token (leaf and operator lanes of a warp run the same instructions): an operator pops
+    // its two children and pushes itself, a leaf pushes itself; defects only set flags, the stack pointer is kept in
+    // range by clamping, and the verdict is formed after the loop.
     int sp = 0;
+    int first = 0;  // the first defect met (scanning from the last token) wins, token checks before shape checks
     for (int i = n - 1; i >= 0; --i) {
       const uint32_t t = tok[i];
-      if (t < 0x80) {
-        if ((int)t >= n_symbols) { status = BOSOT_TREE_BAD_TOKEN; break; }
-        if (sp >= kMaxLeaves) { status = BOSOT_TREE_BAD_SHAPE; break; }
-        st[sp++] = (uint8_t)t;
-      } else {
-        if (t > BOSOT_OP_MUL) { status = BOSOT_TREE_BAD_TOKEN; break; }
-        if (sp < 2 || n_int >= kMaxInternal) { status = BOSOT_TREE_BAD_SHAPE; break; }
-        const uint32_t a = st[sp - 1], b = st[sp - 2];
-        sp -= 2;
-        iid[n_int] = (uint64_t)(a | (b << 8) | ((t - 0x7f) << 16));  // children + operator, replaced by the id in pass 2
-        st[sp++] = (uint8_t)(0x80 | n_int);
-        ++n_int;
-      }
+      const bool is_op = t >= 0x80;
+      const bool bad_tok = is_op ? (t > BOSOT_OP_MUL) : ((int)t >= n_symbols);
+      const bool bad_shape = is_op ? (sp < 2 || n_int >= kMaxInternal) : (sp >= kMaxLeaves);
+      first = first ? first : (bad_tok ? BOSOT_TREE_BAD_TOKEN : (bad_shape ? BOSOT_TREE_BAD_SHAPE : 0));
+      const uint32_t a = st[max(sp - 1, 0)], b = st[max(sp - 2, 0)];
+      const int slot = min(n_int, kMaxInternal - 1);
+      if (is_op) iid[slot] = (uint64_t)(a | (b << 8) | ((t - 0x7f) << 16));  // children + operator, replaced by the id in pass 2
+      sp = is_op ? max(sp - 2, 0) : min(sp, kMaxLeaves - 1);
+      st[sp++] = is_op ? (uint8_t)(0x80 | slot) : (uint8_t)t;
+      n_int += is_op ? 1 : 0;
     }
-    if (status == 0 && sp != 1) status = BOSOT_TREE_BAD_SHAPE;
+    status = first ? first : (sp != 1 ? BOSOT_TREE_BAD_SHAPE : 0);
+    if (status) n_int = 0;
     if (status == 0) {
       for (int r = 0; r < n_int; ++r) {
         const uint32_t packed = (uint32_t)iid[r];
@@ -110,19 +112,21 @@ __device__ __forceinline__ int scan_tree(uint8_t* rec, int n_symbols) {
         const uint64_t ib = (b & 0x80) ? iid[b & 0x7f] : leaf_class(b);
         iid[r] = class_combine(op, ia, ib);
       }
+      // Pass 3, branch-free per token: an operator pushes the state its right child inherits, a leaf records
+      // (symbol, state) and pops the state of the next pending right child.
       sp = 0;
       uint32_t cur = 0;
       for (int i = 0; i < n; ++i) {
         const uint32_t t = tok[i];
-        if (t >= 0x80) {
-          cur = path_child_code(cur, t & 1);
-          st[sp++] = (uint8_t)cur;  // pending right child inherits the same state
-        } else {
-          lsym[n_leaf] = (uint8_t)t;
-          lcode[n_leaf] = (uint8_t)cur;
-          ++n_leaf;
-          if (sp > 0) cur = st[--sp];
-        }
+        const bool is_op = t >= 0x80;
+        const uint32_t child = path_child_code(cur, t & 1);
+        const uint32_t popped = st[max(sp - 1, 0)];
+        lsym[n_leaf] = (uint8_t)t;       // overwritten by the next leaf when this token is an operator
+        lcode[n_leaf] = (uint8_t)cur;
+        n_leaf += is_op ? 0 : 1;
+        if (is_op) st[sp] = (uint8_t)child;
+        cur = is_op ? child : (sp > 0 ? popped : cur);
+        sp += is_op ? 1 : (sp > 0 ? -1 : 0);
       }
     }
   }
