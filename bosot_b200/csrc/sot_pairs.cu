@@ -498,8 +498,12 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
 #pragma unroll
           for (int i = 0; i < kG; ++i) {
             const int r = r0 + i, e = eb + 32 * r;
-            // padding columns of the Gram row stay finite (the posterior kernel may read them)
-            if (r < R && e < ld_i) p.K[row + e] = e < E ? p.variance * x[i] : 0.0;
+            if (r < R) {
+              // R = ceil(E / 32) when there is one tile (R < kMaxR): every row but the last lies inside E
+              if (R < kMaxR && r < R - 1) p.K[row + e] = p.variance * x[i];
+              // padding columns of the Gram row stay finite (the posterior kernel may read them)
+              else if (e < ld_i) p.K[row + e] = e < E ? p.variance * x[i] : 0.0;
+            }
           }
         }
       }
