@@ -7,8 +7,10 @@ candidates/sec at 1/2/4/8 B200 vs host-CPU ref").
 
 One "step" = one pass of the hot path over the whole candidate pool: flat trees -> in-SM
 featurisation -> SOT pair distances against the evaluated set -> Gram -> GP posterior mean/variance
--> Expected Improvement, then ONE NCCL all-gather of the EI vector when the pool is row-sharded
-over several GPUs (strong scaling: the pool is fixed, BASELINE.json config 5).
+-> Expected Improvement.  When the pool is row-sharded over several GPUs (strong scaling: the pool is
+fixed, BASELINE.json config 5) every rank ends with the whole EI vector: by default the posterior kernel
+stores its EI values straight into every GPU's vector over NVLink peer memory and the step closes with one
+symmetric-memory barrier (--collective fused); --collective nccl uses ONE all-gather after the kernel.
 
 Workload (config.workload): "c5_stress_1M_x_200" = 1,000,000 random grammar trees (depth <= 5,
 CKSHighDimSearchSpace d=5) x 200 evaluated trees, hyper-parameters H1 of SURVEY.md 8d.  The C4
