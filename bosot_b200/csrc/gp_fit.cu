@@ -12,6 +12,7 @@
 // Gradients are returned with respect to the CONSTRAINED quantities (w_f treated as independent, ls,
 // var, noise, c); the host applies the chain rule of the sigmoid / softplus transforms.
 #include "sot_common.cuh"
+#include <atomic>
 #include "launch.cuh"
 
 namespace bosot {
@@ -191,7 +192,7 @@ extern "C" int bosot_gp_nll_grad(const double* d_Df, int n_eval, int64_t ld, con
   p.w[0] = weights[0]; p.w[1] = weights[1]; p.w[2] = weights[2];
   p.ls = lengthscale; p.var = variance; p.noise = noise_variance; p.c = mean_c; p.out = d_out9;
   const size_t smem = sizeof(double) * ((size_t)n_eval * (n_eval | 1) + 3 * (size_t)n_eval + 8);
-  static bool attr_set[64] = {false};
+  static std::atomic<bool> attr_set[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
   int dev = 0;
   cudaGetDevice(&dev);
   if (!(dev < 64 && attr_set[dev])) {

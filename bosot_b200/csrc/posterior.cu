@@ -19,6 +19,7 @@
 // from a shared work counter, largest block first, so the triangular cost profile balances itself;
 // partial sums go to a per-block slot and are added in block order => bitwise reproducible.
 #include "sot_common.cuh"
+#include <atomic>
 #include "launch.cuh"
 
 namespace bosot {
@@ -593,7 +594,7 @@ int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_ev
   // warp-specialised TMA variant: needs 16-byte aligned rows of whole 16-byte units
   const bool tma_ok = (ld % 2 == 0) && (n_eval % 2 == 0 || ld > n_eval) && !(reinterpret_cast<uintptr_t>(d_Kstar) & 15);
   if (tma_ok) {
-    static bool ws_attr[64] = {false};
+    static std::atomic<bool> ws_attr[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
     if (!(dev < 64 && ws_attr[dev])) {
       if (int rc = cuda_check(cudaFuncSetAttribute(posterior_ws_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
                               "cudaFuncSetAttribute(posterior_ws_kernel<64>)")) return rc;
@@ -625,7 +626,7 @@ int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_ev
   const int n_blk = (n_eval + kRowBlk - 1) / kRowBlk;
   const size_t smem = sizeof(double) * ((size_t)kPostCand * post_tile_ld(n_eval) + (size_t)n_blk * kPostCand + kPostCand) + 16;
   if (smem > smem_cap) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: n_eval too large for shared memory");
-  static bool attr_set[64] = {false};
+  static std::atomic<bool> attr_set[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
   if (!(dev < 64 && attr_set[dev])) {
     if (int rc = cuda_check(cudaFuncSetAttribute(posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
                             "cudaFuncSetAttribute(posterior_kernel)")) return rc;

@@ -25,6 +25,7 @@
 //                                      combine, exp, store.  The next tree's record is prefetched
 //                                      into registers while the current one is processed.
 #include "sot_common.cuh"
+#include <atomic>
 #include "launch.cuh"
 #include "fast_math.cuh"
 
@@ -511,7 +512,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   }
 }
 
-static bool g_recip_ready[64] = {false};  // per device
+static std::atomic<bool> g_recip_ready[64];  // per device, zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
 
 static int ensure_recip_table() {
   int dev = 0;
@@ -521,7 +522,7 @@ static int ensure_recip_table() {
   h[0] = 0.0;
   for (int t = 1; t < 64; ++t) h[t] = 1.0 / (double)t;
   if (int rc = cuda_check(cudaMemcpyToSymbol(c_recip, h, sizeof(h)), "cudaMemcpyToSymbol(c_recip)")) return rc;
-  static double frac[33 * 33];  // count / total like the reference's float(a) / float(b) (optimal_transport_mappings.py:104-106)
+  double frac[33 * 33];  // count / total like the reference's float(a) / float(b) (optimal_transport_mappings.py:104-106)
   for (int c = 0; c < 33; ++c)
     for (int t = 0; t < 33; ++t) frac[c * 33 + t] = t ? (double)c / (double)t : 0.0;
   if (int rc = cuda_check(cudaMemcpyToSymbol(g_frac, frac, sizeof(frac)), "cudaMemcpyToSymbol(g_frac)")) return rc;
@@ -565,7 +566,7 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   if (int rc = cuda_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return rc;
 
   // launch 1: scan
-  static bool scan_attr[64] = {false};
+  static std::atomic<bool> scan_attr[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
   if (!(dev < 64 && scan_attr[dev])) {
     if (int rc = cuda_check(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanThreads * kRecBytes),
                             "cudaFuncSetAttribute(scan_kernel)")) return rc;
@@ -600,7 +601,7 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
       {sot_pair_kernel<5, false>, sot_pair_kernel<5, true>}, {sot_pair_kernel<6, false>, sot_pair_kernel<6, true>},
       {sot_pair_kernel<7, false>, sot_pair_kernel<7, true>}, {sot_pair_kernel<8, false>, sot_pair_kernel<8, true>}};
   KernelFn kernel = table[R - 1][extra ? 1 : 0];
-  static bool attr_set[64] = {false};
+  static std::atomic<bool> attr_set[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
   if (!(dev < 64 && attr_set[dev])) {
     for (int r = 0; r < kMaxR; ++r)
       for (int x = 0; x < 2; ++x)
