@@ -17,15 +17,20 @@
 //                                      written as compact records (coalesced) to global memory
 //   sot_pair_kernel  warp-per-tree   : phase B  dedupe with __match_any_sync; operator classes go
 //                                      through the hash table, reduced paths through a direct table,
-//                                      and their (short) posting lists are walked into shared-memory
-//                                      accumulators;
+//                                      and their (short) posting lists are walked as one flattened list
+//                                      (segment of a posting found by a warp OR-reduction, no search)
+//                                      into shared-memory accumulators; the candidate's DIM_WISE vector
+//                                      and its L1 distance to every distinct block vector ("state") of
+//                                      the evaluated set;
 //                                      phase C  every lane owns R evaluated trees in registers:
 //                                      leaf-symbol classes (dense: most symbols occur in most trees)
-//                                      against the transposed count table, DIM_WISE dense L1,
-//                                      combine, exp, store.  The next tree's record is prefetched
-//                                      into registers while the current one is processed.
-#include "sot_common.cuh"
+//                                      against the packed transposed count table (two trees per 32-bit
+//                                      lane), DIM_WISE as one table lookup per (pair, block) or the dense
+//                                      column loop, then combine, exp and store in groups of four pairs.
+//                                      The next tree's record is prefetched into registers while the
+//                                      current one is processed.
 #include <atomic>
+#include "sot_common.cuh"
 #include "launch.cuh"
 #include "fast_math.cuh"
 
