@@ -1,0 +1,31 @@
+"""SASS listings of the hot kernels from the built library (cuobjdump), with the control-word column stripped, plus an
+opcode histogram per kernel.  Usage: python profiles/tools_sass.py <tag>   ->  profiles/<tag>_sass_<kernel>.txt"""
+import collections
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "bosot_b200", "libbosot_b200.so")
+KERNELS = {
+    "scan_kernel": "_ZN5bosot11scan_kernelEPKhliPhPi",
+    "sot_pair_kernel_R7": "_ZN5bosot15sot_pair_kernelILi7ELb0EEEvNS_10PairParamsE13bosot_grammar",
+    "posterior_ws_kernel_TC64": "_ZN5bosot19posterior_ws_kernelILi64EEEvNS_10PostParamsE",
+}
+tag = sys.argv[1] if len(sys.argv) > 1 else "sass"
+for name, sym in KERNELS.items():
+    out = subprocess.run(["cuobjdump", "-sass", "-fun", sym, LIB], capture_output=True, text=True).stdout
+    lines = [re.sub(r"\s*/\* 0x[0-9a-f]{16} \*/\s*$", "", l.rstrip()) for l in out.splitlines() if re.match(r"^\s+/\*[0-9a-f]{4}\*/", l)]
+    ops = collections.Counter()
+    for l in lines:
+        m = re.match(r"^\s+/\*[0-9a-f]{4}\*/\s+(@!?U?P\w+\s+)?([A-Z0-9_.]+)", l)
+        if m:
+            ops[m.group(2)] += 1
+    path = os.path.join(ROOT, "profiles", "%s_sass_%s.txt" % (tag, name))
+    with open(path, "w") as f:
+        f.write("# %s (%s), sm_100a, %d instructions (static)\n# opcode histogram:\n" % (name, sym, len(lines)))
+        for op, n in ops.most_common():
+            f.write("#   %-28s %5d\n" % (op, n))
+        f.write("\n".join(lines) + "\n")
+    print(path, len(lines), {k: ops[k] for k in ops if any(t in k for t in ("UBLKCP", "DMMA", "VIMNMX.U16x2", "REDUX", "MATCH", "SYNCS", "ATOMS"))})
