@@ -1,6 +1,7 @@
 // C-ABI glue: error state, launch bookkeeping, argument checks and the composed
 // "acquire" entry points (pairs -> posterior -> acquisition) with host or device buffers.
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <cstdio>
 #include <cstring>
@@ -202,8 +203,9 @@ extern "C" int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const 
   int32_t* d_status = reinterpret_cast<int32_t*>(w + W.off_status);
   uint8_t* d_recs = w + W.off_recs;
 
-  int n_chunks = (int)(n_cand / 200000);
-  if (n_chunks > kMaxChunks) n_chunks = kMaxChunks;
+  static const int64_t chunk_env = getenv("BOSOT_E2E_CHUNK") ? atoll(getenv("BOSOT_E2E_CHUNK")) : 0;  // measurement switch
+  int n_chunks = (int)(n_cand / (chunk_env > 0 ? chunk_env : 200000));
+  if (n_chunks > kMaxChunks - 1) n_chunks = kMaxChunks - 1;
   if (n_chunks <= 1) {
     // small pool: nothing to overlap, keep everything on the caller's stream (no cross-stream event hops)
     if (int rc = cuda_check(cudaMemcpyAsync(d_trees, h_trees, (size_t)n_cand * kTreeBytes, cudaMemcpyHostToDevice, st), "H2D trees")) return rc;
@@ -228,10 +230,13 @@ extern "C" int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const 
   if (int rc = cuda_check(cudaEventRecord(P->start, st), "cudaEventRecord")) return rc;
   if (int rc = cuda_check(cudaStreamWaitEvent(P->h2d, P->start, 0), "cudaStreamWaitEvent")) return rc;
   if (int rc = cuda_check(cudaStreamWaitEvent(P->d2h, P->start, 0), "cudaStreamWaitEvent")) return rc;
-  for (int k = 0; k < n_chunks; ++k) {
-    const int64_t c0 = (int64_t)k * per;
+  // the first chunk is a quarter of the others: the kernels start after a quarter of the copy time (pipeline fill)
+  const int64_t first = (per / 4 + 63) & ~(int64_t)63;
+  for (int k = 0; k < n_chunks + 1 && k < kMaxChunks; ++k) {
+    const int64_t c0 = k == 0 ? 0 : first + (int64_t)(k - 1) * per;
     if (c0 >= n_cand) break;
-    const int64_t n = (c0 + per <= n_cand) ? per : n_cand - c0;
+    const int64_t len = k == 0 ? first : per;
+    const int64_t n = (c0 + len <= n_cand) ? len : n_cand - c0;
     if (int rc = cuda_check(cudaMemcpyAsync(d_trees + c0 * kTreeBytes, h_trees + c0 * kTreeBytes, (size_t)n * kTreeBytes,
                                             cudaMemcpyHostToDevice, P->h2d), "H2D trees")) return rc;
     if (int rc = cuda_check(cudaEventRecord(P->copied[k], P->h2d), "cudaEventRecord")) return rc;

@@ -57,7 +57,16 @@ def timed(fn):
     return float(np.median(ts)), float(np.min(ts))
 
 
+h_ca = ca.cpu().pin_memory()
+h_ei = torch.empty(pool, dtype=torch.float64).pin_memory()
+
+
+def k_e2e():
+    eng.acquire_host(h_ca, h_ei, sync=True)
+
+
 print("info", eng.state.info())
 print("pairs  ms median %.4f min %.4f" % timed(k_pairs))
 print("post   ms median %.4f min %.4f" % timed(k_post))
+print("e2e    ms median %.4f min %.4f" % timed(k_e2e))
 print("check  ei sum %.12e  sigma nan %d" % (float(ei.sum()), int(torch.isnan(sg).sum())))
