@@ -256,6 +256,11 @@ def test_full_size_properties(n_cand, n_eval):
     mu, sigma, ei = eng.acquire_device(XC)
     mu_p, sigma_p, ei_p = eng.acquire_device(XC[perm].contiguous())
     assert torch.equal(mu[perm], mu_p) and torch.equal(sigma[perm], sigma_p) and torch.equal(ei[perm], ei_p)
+    # 3b. the host-buffer entry point (chunked three-stream pipeline at this size) returns the same bits
+    h_trees = torch.from_numpy(ca_np).pin_memory()
+    h_acq, h_mu, h_sig = (torch.empty(n_cand, dtype=torch.float64).pin_memory() for _ in range(3))
+    eng.acquire_host(h_trees, h_acq, h_mu, h_sig)
+    assert torch.equal(h_acq, ei.cpu()) and torch.equal(h_mu, mu.cpu()) and torch.equal(h_sig, sigma.cpu())
     # 4. posterior at planted copies reproduces the posterior at the evaluated kernels
     assert torch.equal(mu[idx], eng.mu_data) and torch.equal(sigma[idx], eng.sigma_data)
     assert float(sigma.min()) > 0 and float(sigma.max()) <= np.sqrt(hyp.variance) * (1 + 1e-12)
