@@ -104,6 +104,37 @@ extern "C" size_t bosot_acquire_work_bytes(int64_t n_cand, int n_eval) {
   return work_layout(n_cand, n_eval).total;
 }
 
+// helper streams / events for the pipelined host entry point (created lazily, one set per device, never destroyed)
+namespace bosot {
+constexpr int kMaxChunks = 16;
+struct HostPipe {
+  bool ready = false;
+  cudaStream_t h2d = nullptr, d2h = nullptr, alt = nullptr;  // alt: second compute stream (odd chunks)
+  cudaEvent_t start = nullptr, done = nullptr, copied[kMaxChunks] = {}, computed[kMaxChunks] = {};
+};
+static HostPipe g_pipe[64];
+static std::mutex g_pipe_mutex;  // the helper events are per device: serialise the (short) enqueue section
+
+static int host_pipe(int dev, HostPipe** out) {
+  if (dev < 0 || dev >= 64) return set_error(BOSOT_EINVAL, "bosot_acquire_host: device index out of range");
+  HostPipe& P = g_pipe[dev];
+  if (!P.ready) {
+    if (int rc = cuda_check(cudaStreamCreateWithFlags(&P.h2d, cudaStreamNonBlocking), "cudaStreamCreate(h2d)")) return rc;
+    if (int rc = cuda_check(cudaStreamCreateWithFlags(&P.d2h, cudaStreamNonBlocking), "cudaStreamCreate(d2h)")) return rc;
+    if (int rc = cuda_check(cudaStreamCreateWithFlags(&P.alt, cudaStreamNonBlocking), "cudaStreamCreate(alt)")) return rc;
+    if (int rc = cuda_check(cudaEventCreateWithFlags(&P.start, cudaEventDisableTiming), "cudaEventCreate")) return rc;
+    if (int rc = cuda_check(cudaEventCreateWithFlags(&P.done, cudaEventDisableTiming), "cudaEventCreate")) return rc;
+    for (int k = 0; k < kMaxChunks; ++k) {
+      if (int rc = cuda_check(cudaEventCreateWithFlags(&P.copied[k], cudaEventDisableTiming), "cudaEventCreate")) return rc;
+      if (int rc = cuda_check(cudaEventCreateWithFlags(&P.computed[k], cudaEventDisableTiming), "cudaEventCreate")) return rc;
+    }
+    P.ready = true;
+  }
+  *out = &P;
+  return BOSOT_OK;
+}
+}  // namespace bosot
+
 extern "C" int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,
                                     const void* d_eval_blob, int n_eval, const double weights[3],
                                     double variance, double lengthscale,
@@ -119,6 +150,7 @@ extern "C" int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, cons
   double* K = reinterpret_cast<double*>(w + W.off_K);
   int32_t* status = reinterpret_cast<int32_t*>(w + W.off_status);
   cudaStream_t st = (cudaStream_t)stream;
+  // one set of launches: cutting a device-resident pool into chunks on two streams was measured slower (4.07 vs 3.95 ms)
   if (int rc = launch_pairs(d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale, K, nullptr,
                             nullptr, W.ld, status, w + W.off_recs, pairs_scratch_bytes(n_cand), st)) return rc;
   return launch_posterior(K, n_cand, W.ld, n_eval, d_Linv, ldl, d_beta, mean_c, variance, acq_kind, d_current_max, xi,
@@ -146,36 +178,6 @@ extern "C" int bosot_acquire_device_scatter(const uint8_t* d_trees, int64_t n_ca
   return launch_posterior(K, n_cand, W.ld, n_eval, d_Linv, ldl, d_beta, mean_c, variance, acq_kind, d_current_max, xi,
                           ucb_beta, d_mu, d_sigma, d_acq, st, static_cast<double* const*>(d_peer_ptrs), n_peers, peer_offset);
 }
-
-// helper streams / events for the pipelined host entry point (created lazily, one set per device, never destroyed)
-namespace bosot {
-constexpr int kMaxChunks = 16;
-struct HostPipe {
-  bool ready = false;
-  cudaStream_t h2d = nullptr, d2h = nullptr;
-  cudaEvent_t start = nullptr, done = nullptr, copied[kMaxChunks] = {}, computed[kMaxChunks] = {};
-};
-static HostPipe g_pipe[64];
-static std::mutex g_pipe_mutex;  // the helper events are per device: serialise the (short) enqueue section
-
-static int host_pipe(int dev, HostPipe** out) {
-  if (dev < 0 || dev >= 64) return set_error(BOSOT_EINVAL, "bosot_acquire_host: device index out of range");
-  HostPipe& P = g_pipe[dev];
-  if (!P.ready) {
-    if (int rc = cuda_check(cudaStreamCreateWithFlags(&P.h2d, cudaStreamNonBlocking), "cudaStreamCreate(h2d)")) return rc;
-    if (int rc = cuda_check(cudaStreamCreateWithFlags(&P.d2h, cudaStreamNonBlocking), "cudaStreamCreate(d2h)")) return rc;
-    if (int rc = cuda_check(cudaEventCreateWithFlags(&P.start, cudaEventDisableTiming), "cudaEventCreate")) return rc;
-    if (int rc = cuda_check(cudaEventCreateWithFlags(&P.done, cudaEventDisableTiming), "cudaEventCreate")) return rc;
-    for (int k = 0; k < kMaxChunks; ++k) {
-      if (int rc = cuda_check(cudaEventCreateWithFlags(&P.copied[k], cudaEventDisableTiming), "cudaEventCreate")) return rc;
-      if (int rc = cuda_check(cudaEventCreateWithFlags(&P.computed[k], cudaEventDisableTiming), "cudaEventCreate")) return rc;
-    }
-    P.ready = true;
-  }
-  *out = &P;
-  return BOSOT_OK;
-}
-}  // namespace bosot
 
 // Host buffers in, host buffers out.  Large pools are cut into chunks that flow through a three-stage
 // pipeline on three streams -- H2D of chunk k+1 (copy engine) | kernels of chunk k (caller's stream) |
@@ -230,6 +232,10 @@ extern "C" int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const 
   if (int rc = cuda_check(cudaEventRecord(P->start, st), "cudaEventRecord")) return rc;
   if (int rc = cuda_check(cudaStreamWaitEvent(P->h2d, P->start, 0), "cudaStreamWaitEvent")) return rc;
   if (int rc = cuda_check(cudaStreamWaitEvent(P->d2h, P->start, 0), "cudaStreamWaitEvent")) return rc;
+  if (int rc = cuda_check(cudaStreamWaitEvent(P->alt, P->start, 0), "cudaStreamWaitEvent")) return rc;
+  // Chunks alternate between the caller's stream and a second compute stream: the persistent kernels of chunk k+1
+  // take over the SMs that the tail of chunk k has already left (every chunk has its own slice of the work buffer).
+  static const bool two_streams = !(getenv("BOSOT_E2E_ONE_STREAM") && atoi(getenv("BOSOT_E2E_ONE_STREAM")));
   // the first chunk is a quarter of the others: the kernels start after a quarter of the copy time (pipeline fill)
   const int64_t first = (per / 4 + 63) & ~(int64_t)63;
   for (int k = 0; k < n_chunks + 1 && k < kMaxChunks; ++k) {
@@ -240,14 +246,15 @@ extern "C" int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const 
     if (int rc = cuda_check(cudaMemcpyAsync(d_trees + c0 * kTreeBytes, h_trees + c0 * kTreeBytes, (size_t)n * kTreeBytes,
                                             cudaMemcpyHostToDevice, P->h2d), "H2D trees")) return rc;
     if (int rc = cuda_check(cudaEventRecord(P->copied[k], P->h2d), "cudaEventRecord")) return rc;
-    if (int rc = cuda_check(cudaStreamWaitEvent(st, P->copied[k], 0), "cudaStreamWaitEvent")) return rc;
+    cudaStream_t cs = (two_streams && (k & 1)) ? P->alt : st;
+    if (int rc = cuda_check(cudaStreamWaitEvent(cs, P->copied[k], 0), "cudaStreamWaitEvent")) return rc;
     if (int rc = launch_pairs(d_trees + c0 * kTreeBytes, n, grammar, d_eval_blob, n_eval, weights, variance, lengthscale,
                               d_K + c0 * W.ld, nullptr, nullptr, W.ld, d_status + c0, d_recs + (size_t)c0 * kScanBytes,
-                              pairs_scratch_bytes(n), st)) return rc;
+                              pairs_scratch_bytes(n), cs)) return rc;
     if (int rc = launch_posterior(d_K + c0 * W.ld, n, W.ld, n_eval, d_Linv, ldl, d_beta, mean_c, variance, acq_kind, d_current_max,
                                   xi, ucb_beta, h_mu ? d_mu + c0 : nullptr, h_sigma ? d_sigma + c0 : nullptr,
-                                  h_acq ? d_acq + c0 : nullptr, st)) return rc;
-    if (int rc = cuda_check(cudaEventRecord(P->computed[k], st), "cudaEventRecord")) return rc;
+                                  h_acq ? d_acq + c0 : nullptr, cs)) return rc;
+    if (int rc = cuda_check(cudaEventRecord(P->computed[k], cs), "cudaEventRecord")) return rc;
     if (int rc = cuda_check(cudaStreamWaitEvent(P->d2h, P->computed[k], 0), "cudaStreamWaitEvent")) return rc;
     const size_t nb = sizeof(double) * (size_t)n;
     if (h_mu) if (int rc = cuda_check(cudaMemcpyAsync(h_mu + c0, d_mu + c0, nb, cudaMemcpyDeviceToHost, P->d2h), "D2H mu")) return rc;

@@ -68,5 +68,6 @@ def k_e2e():
 print("info", eng.state.info())
 print("pairs  ms median %.4f min %.4f" % timed(k_pairs))
 print("post   ms median %.4f min %.4f" % timed(k_post))
+print("device ms median %.4f min %.4f" % timed(lambda: eng.acquire_device(ca, out=(mu, sg, ei))))
 print("e2e    ms median %.4f min %.4f" % timed(k_e2e))
 print("check  ei sum %.12e  sigma nan %d" % (float(ei.sum()), int(torch.isnan(sg).sum())))
