@@ -24,6 +24,7 @@ OP_ADD = 0x80
 OP_MUL = 0x81
 PAD = 0xFF
 ACQ_NONE, ACQ_EI, ACQ_UCB = 0, 1, 2
+ERAW = -4  # bosot_host_*: block of raw generator outputs too short
 
 
 class BosotGrammar(C.Structure):
@@ -101,6 +102,8 @@ SIGNATURES = {
          _P, C.c_size_t, _P, _P, _P, _P, C.c_int, C.c_int64, _P],
     ),
     "bosot_neighbours": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P, _P]),
+    "bosot_host_choices": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
+    "bosot_host_recursive_dataset": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, C.c_int, _P, C.POINTER(C.c_int64)]),
     "bosot_gp_fit_max_eval": (C.c_int, []),
     "bosot_gp_nll_grad": (C.c_int, [_P, C.c_int, C.c_int64, _P, _D3, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P]),
     "bosot_hellinger_record_doubles": (C.c_int, [C.c_int]),

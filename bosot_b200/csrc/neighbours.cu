@@ -14,6 +14,48 @@
 
 namespace bosot {
 
+// one move on one record (host and device): res = neighbour number k of rec; returns 0 or a defect code
+__host__ __device__ inline int neighbour_move(const uint8_t* rec, int64_t k, int B, uint8_t* res) {
+  for (int q = 0; q < kTreeBytes; ++q) res[q] = BOSOT_PAD;
+  const int n = rec[0];
+  if (n < 1 || n > kMaxNodes || !(n & 1)) return BOSOT_TREE_BAD_LENGTH;
+  const int L = (n + 1) >> 1;
+  const int64_t n_leaf_moves = (int64_t)L * B;
+  if (k < 0 || k >= n_leaf_moves + (int64_t)n * 2 * B) return BOSOT_NEIGHBOUR_BAD_INDEX;
+  if (k < n_leaf_moves) {
+    const int which = (int)(k / B), sym = (int)(k % B);
+    int seen = 0;
+    for (int p = 1; p <= n; ++p) {
+      uint8_t t = rec[p];
+      if (t < 0x80) {
+        if (seen == which) t = (uint8_t)sym;
+        ++seen;
+      }
+      res[p] = t;
+    }
+    res[0] = (uint8_t)n;
+    return seen != L ? BOSOT_TREE_BAD_SHAPE : 0;
+  }
+  if (n + 2 > kMaxNodes) return BOSOT_NEIGHBOUR_TOO_BIG;
+  const int64_t kk = k - n_leaf_moves;
+  const int node = (int)(kk / (2 * B));  // pre-order position, 0 = root
+  const int op = (int)((kk % (2 * B)) / B), sym = (int)(kk % B);
+  int end = node, pending = 1;           // last token of the sub-expression rooted at `node`
+  for (int p = node; p < n; ++p) {
+    pending += (rec[1 + p] >= 0x80) ? 1 : -1;
+    if (pending == 0) { end = p; break; }
+  }
+  if (pending != 0) return BOSOT_TREE_BAD_SHAPE;
+  int w = 1;
+  for (int p = 0; p < node; ++p) res[w++] = rec[1 + p];
+  res[w++] = (uint8_t)(BOSOT_OP_ADD + op);
+  for (int p = node; p <= end; ++p) res[w++] = rec[1 + p];
+  res[w++] = (uint8_t)sym;
+  for (int p = end + 1; p < n; ++p) res[w++] = rec[1 + p];
+  res[0] = (uint8_t)(n + 2);
+  return 0;
+}
+
 __global__ void neighbour_kernel(const uint8_t* __restrict__ trees, int64_t n_trees, const int64_t* __restrict__ index,
                                  int n_symbols, uint8_t* __restrict__ out, int32_t* __restrict__ status) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -22,56 +64,7 @@ __global__ void neighbour_kernel(const uint8_t* __restrict__ trees, int64_t n_tr
   const uint4* src = reinterpret_cast<const uint4*>(trees + i * kTreeBytes);
 #pragma unroll
   for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(rec)[q] = __ldg(src + q);
-#pragma unroll
-  for (int q = 0; q < kTreeBytes; ++q) res[q] = BOSOT_PAD;
-  const int n = rec[0];
-  const int B = n_symbols;
-  int st = 0;
-  if (n < 1 || n > kMaxNodes || !(n & 1)) {
-    st = BOSOT_TREE_BAD_LENGTH;
-  } else {
-    const int L = (n + 1) >> 1;
-    const int64_t k = index[i];
-    const int64_t n_leaf_moves = (int64_t)L * B;
-    if (k < 0 || k >= n_leaf_moves + (int64_t)n * 2 * B) {
-      st = BOSOT_NEIGHBOUR_BAD_INDEX;
-    } else if (k < n_leaf_moves) {
-      const int which = (int)(k / B), sym = (int)(k % B);
-      int seen = 0;
-      for (int p = 1; p <= n; ++p) {
-        uint8_t t = rec[p];
-        if (t < 0x80) {
-          if (seen == which) t = (uint8_t)sym;
-          ++seen;
-        }
-        res[p] = t;
-      }
-      res[0] = (uint8_t)n;
-      if (seen != L) st = BOSOT_TREE_BAD_SHAPE;
-    } else if (n + 2 > kMaxNodes) {
-      st = BOSOT_NEIGHBOUR_TOO_BIG;
-    } else {
-      const int64_t kk = k - n_leaf_moves;
-      const int node = (int)(kk / (2 * B));  // pre-order position, 0 = root
-      const int op = (int)((kk % (2 * B)) / B), sym = (int)(kk % B);
-      int end = node, pending = 1;           // last token of the sub-expression rooted at `node`
-      for (int p = node; p < n; ++p) {
-        pending += (rec[1 + p] >= 0x80) ? 1 : -1;
-        if (pending == 0) { end = p; break; }
-      }
-      if (pending != 0) {
-        st = BOSOT_TREE_BAD_SHAPE;
-      } else {
-        int w = 1;
-        for (int p = 0; p < node; ++p) res[w++] = rec[1 + p];
-        res[w++] = (uint8_t)(BOSOT_OP_ADD + op);
-        for (int p = node; p <= end; ++p) res[w++] = rec[1 + p];
-        res[w++] = (uint8_t)sym;
-        for (int p = end + 1; p < n; ++p) res[w++] = rec[1 + p];
-        res[0] = (uint8_t)(n + 2);
-      }
-    }
-  }
+  const int st = neighbour_move(rec, index[i], n_symbols, res);
   if (st) {  // leave the input unchanged in the output slot so downstream kernels stay well defined
 #pragma unroll
     for (int q = 0; q < kTreeBytes; ++q) res[q] = rec[q];
@@ -82,7 +75,73 @@ __global__ void neighbour_kernel(const uint8_t* __restrict__ trees, int64_t n_tr
   if (status) status[i] = st;
 }
 
+// ---- host side of the candidate producers: the reference draws every neighbour number with np.random.choice(n),
+// one call per offspring, in a data-dependent order.  To propose the same kernels from the same seed the draws are
+// replayed here from a block of raw 32-bit outputs of NumPy's global generator: RandomState.choice(n) = randint(0, n)
+// = masked rejection on 32-bit outputs (mask = next power of two minus one, redraw while value > n - 1; no draw at
+// all for n == 1).  The caller advances the global generator by the number of outputs consumed.
+static inline bool legacy_choice(const uint32_t* raw, int64_t n_raw, int64_t& pos, int64_t n, int64_t& out) {
+  const uint64_t rng = (uint64_t)n - 1;
+  if (rng == 0) { out = 0; return true; }
+  uint64_t mask = rng;
+  mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+  while (true) {
+    if (pos >= n_raw) return false;
+    const uint64_t v = raw[pos++] & mask;
+    if (v <= rng) { out = (int64_t)v; return true; }
+  }
+}
+
+static inline int64_t neighbour_count(const uint8_t* rec, int B) {  // kernel_grammar_search_spaces.py:97-106
+  const int64_t n = rec[0];
+  return ((n + 1) / 2) * B + n * 2 * B;
+}
+
 }  // namespace bosot
+
+extern "C" int bosot_host_choices(const uint32_t* h_raw, int64_t n_raw, const int64_t* h_n, int64_t count, int64_t* h_out,
+                                  int64_t* h_consumed) {
+  using namespace bosot;
+  if (!h_raw || !h_n || !h_out || !h_consumed || n_raw < 0 || count < 0) return set_error(BOSOT_EINVAL, "bosot_host_choices: bad argument");
+  int64_t pos = 0;
+  for (int64_t i = 0; i < count; ++i) {
+    if (h_n[i] < 1 || h_n[i] > 0x100000000LL) return set_error(BOSOT_EINVAL, "bosot_host_choices: population size out of range");
+    if (!legacy_choice(h_raw, n_raw, pos, h_n[i], h_out[i])) return BOSOT_ERAW;
+  }
+  *h_consumed = pos;
+  return BOSOT_OK;
+}
+
+extern "C" int bosot_host_recursive_dataset(const uint32_t* h_raw, int64_t n_raw, int n_symbols, int64_t n_data, int n_per_step,
+                                            uint8_t* h_pool, int64_t* h_consumed) {
+  using namespace bosot;
+  if (!h_raw || !h_pool || !h_consumed || n_raw < 0 || n_data < 0 || n_per_step < 1)
+    return set_error(BOSOT_EINVAL, "bosot_host_recursive_dataset: bad argument");
+  if (n_symbols < 1 || n_symbols > BOSOT_MAX_SYMBOLS) return set_error(BOSOT_EINVAL, "bosot_host_recursive_dataset: n_symbols out of range");
+  const int B = n_symbols;
+  int64_t len = 0, pos = 0;
+  for (; len < B; ++len) {  // the roots: one leaf per base kernel
+    uint8_t* r = h_pool + len * kTreeBytes;
+    for (int q = 0; q < kTreeBytes; ++q) r[q] = BOSOT_PAD;
+    r[0] = 1;
+    r[1] = (uint8_t)len;
+  }
+  while (len < n_data) {
+    int64_t c = 0;
+    if (!legacy_choice(h_raw, n_raw, pos, len, c)) return BOSOT_ERAW;
+    const uint8_t* chosen = h_pool + c * kTreeBytes;
+    for (int s = 0; s < n_per_step && len < n_data; ++s) {
+      int64_t k = 0;
+      if (!legacy_choice(h_raw, n_raw, pos, neighbour_count(chosen, B), k)) return BOSOT_ERAW;
+      const int st = neighbour_move(chosen, k, B, h_pool + len * kTreeBytes);
+      if (st == BOSOT_NEIGHBOUR_TOO_BIG) return set_error(BOSOT_ETREE, "bosot_host_recursive_dataset: neighbour exceeds the 63-node flat record");
+      if (st) return set_error(BOSOT_ETREE, "bosot_host_recursive_dataset: malformed record");
+      ++len;
+    }
+  }
+  *h_consumed = pos;
+  return BOSOT_OK;
+}
 
 extern "C" int bosot_neighbours(const uint8_t* d_trees, int64_t n_trees, const int64_t* d_index, int n_symbols,
                                 uint8_t* d_out, int32_t* d_status, void* stream) {

@@ -77,6 +77,40 @@ def neighbours_device(trees: torch.Tensor, index: torch.Tensor, grammar: Grammar
     return out
 
 
+def _replay_global_rng(call, expected_outputs: int):
+    """Run ``call(raw_ptr, n_raw, consumed_ref) -> rc`` on a block of raw 32-bit outputs of NumPy's GLOBAL generator and
+    leave the generator exactly where the reference's sequence of ``np.random.choice`` calls would have left it:
+    the state is saved, a block of outputs is drawn, the C side reports how many it used, the state is restored and
+    advanced by that many outputs.  The block grows until it is long enough (BOSOT_ERAW)."""
+    n_raw = max(64, 4 * int(expected_outputs))
+    while True:
+        state = np.random.get_state()
+        raw = np.random.randint(0, 2**32, size=n_raw, dtype=np.uint32)
+        consumed = C.c_int64(0)
+        rc = call(raw.ctypes.data, n_raw, C.byref(consumed))
+        np.random.set_state(state)
+        if rc == _lib.ERAW:
+            n_raw *= 4
+            continue
+        _lib.check(rc, "host producer")
+        if consumed.value:
+            np.random.randint(0, 2**32, size=consumed.value, dtype=np.uint32)
+        return
+
+
+def legacy_choices(sizes: np.ndarray) -> np.ndarray:
+    """``[np.random.choice(n) for n in sizes]`` -- same values, same final generator state -- in one native call
+    (C-ABI ``bosot_host_choices``)."""
+    sizes = np.ascontiguousarray(sizes, dtype=np.int64)
+    out = np.empty(len(sizes), dtype=np.int64)
+    if len(sizes) == 0:
+        return out
+    lib = _lib.load()
+    _replay_global_rng(lambda raw, n_raw, used: lib.bosot_host_choices(raw, n_raw, sizes.ctypes.data, len(sizes), out.ctypes.data, used),
+                       2 * len(sizes))
+    return out
+
+
 class FlatCandidateGenerator:
     """Flat-record counterpart of ``KernelGrammarCandidateGenerator`` (reference
     kernel_grammar_candidate_generator.py:27-117) for the two generators the EA uses."""
@@ -90,17 +124,15 @@ class FlatCandidateGenerator:
 
     def get_dataset_recursivly_generated(self, n_data: int, n_per_step: int = 1) -> np.ndarray:
         """Roots first, then repeatedly a random neighbour of a randomly chosen earlier element
-        (:98-111).  Sequential by construction, so it runs on the host; ``np.random.choice`` is called
-        on an index range of the same length as the reference's list, which consumes the stream identically."""
+        (:98-111).  Sequential by construction, so it runs on the host, in native code (C-ABI
+        ``bosot_host_recursive_dataset``) that replays the reference's ``np.random.choice`` draws from raw outputs of
+        the global generator: the same trees from the same seed, the generator left in the same state."""
         B = self.grammar.n_symbols
-        pool = [r for r in self.roots]
-        while len(pool) < n_data:
-            chosen = pool[int(np.random.choice(len(pool)))]
-            for _ in range(n_per_step):
-                if len(pool) < n_data:
-                    k = int(np.random.choice(int(num_neighbours(chosen[None, :], B)[0])))
-                    pool.append(neighbour_at_index_host(chosen, k, B))
-        return np.stack(pool[:max(n_data, B)])
+        pool = np.empty((max(int(n_data), B), _lib.TREE_BYTES), dtype=np.uint8)
+        lib = _lib.load()
+        _replay_global_rng(lambda raw, n_raw, used: lib.bosot_host_recursive_dataset(raw, n_raw, B, int(n_data), int(n_per_step),
+                                                                                      pool.ctypes.data, used), 4 * int(n_data))
+        return pool
 
     def get_initial_for_evolutionary_opt(self, n_initial: int) -> np.ndarray:
         return self.get_dataset_recursivly_generated(n_initial, 1)
@@ -110,7 +142,7 @@ class FlatCandidateGenerator:
         reference's order (survivor-major, :85-93)."""
         counts = num_neighbours(survivors, self.grammar.n_symbols)
         parent = np.repeat(np.arange(len(survivors)), n_around)
-        index = np.array([int(np.random.choice(int(counts[p]))) for p in parent], dtype=np.int64)
+        index = legacy_choices(counts[parent])  # one np.random.choice(count) per offspring in the reference
         return parent, index
 
 

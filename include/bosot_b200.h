@@ -82,7 +82,8 @@ typedef struct bosot_grammar {
 #define BOSOT_OK 0
 #define BOSOT_EINVAL (-1)  /* bad argument (null pointer, size out of range) */
 #define BOSOT_ECUDA (-2)   /* CUDA runtime error, see bosot_last_error() */
-#define BOSOT_ETREE (-3)   /* malformed tree record (only from bosot_check_status) */
+#define BOSOT_ETREE (-3)   /* malformed tree record */
+#define BOSOT_ERAW (-4)    /* bosot_host_*: the block of raw generator outputs is used up, call again with a longer one */
 
 const char* bosot_last_error(void); /* thread-local message of the last failing call */
 int bosot_abi_version(void);
@@ -245,6 +246,22 @@ int bosot_gp_nll_grad(const double* d_Df, int n_eval, int64_t ld, const double* 
  * BOSOT_TREE_* / BOSOT_NEIGHBOUR_* code; on error the input tree is copied through unchanged. */
 int bosot_neighbours(const uint8_t* d_trees, int64_t n_trees, const int64_t* d_index, int n_symbols,
                      uint8_t* d_out, int32_t* d_status, void* stream);
+
+/* Host side of the producers, for seeds that must propose the same kernels as the reference: the reference draws
+ * every random index with np.random.choice(n), one Python call per draw (kernel_grammar_search_spaces.py:144-151,
+ * kernel_grammar_candidate_generator.py:85-111).  These two functions replay exactly those draws from h_raw, a block
+ * of raw 32-bit outputs of the same generator (np.random.randint(0, 2**32, size, dtype=uint32)):
+ * RandomState.choice(n) is a masked rejection on 32-bit outputs (no output is used for n == 1).
+ * *h_consumed = outputs used; the caller restores the generator state and advances it by that many outputs.
+ * Return BOSOT_ERAW when h_raw is too short (nothing is to be kept from such a call).
+ *   bosot_host_choices           out[i] = choice(n[i]), i = 0 .. count-1 in order
+ *   bosot_host_recursive_dataset get_dataset_recursivly_generated(n_data, n_per_step) on flat records: the B roots,
+ *                                then repeatedly a random neighbour of a randomly chosen earlier element;
+ *                                h_pool: [max(n_data, n_symbols)][64] */
+int bosot_host_choices(const uint32_t* h_raw, int64_t n_raw, const int64_t* h_n, int64_t count, int64_t* h_out,
+                       int64_t* h_consumed);
+int bosot_host_recursive_dataset(const uint32_t* h_raw, int64_t n_raw, int n_symbols, int64_t n_data, int n_per_step,
+                                 uint8_t* h_pool, int64_t* h_consumed);
 
 /* ---- Hellinger kernel-kernel --------------------------------------------------
  * The alternative kernel-kernel behind the same BaseObjectKernel API (reference

@@ -38,6 +38,54 @@ def test_flat_generator_consumes_rng_like_object_generator():
     assert [decode_to_name(r, gram) for r in flat] == names and after_obj == after_flat
 
 
+def _python_recursive_dataset(grammar, n_data, n_per_step=1):
+    """The reference's loop (kernel_grammar_candidate_generator.py:98-111) on flat records, one np.random.choice per draw."""
+    B = grammar.n_symbols
+    roots = np.full((B, 64), 0xFF, dtype=np.uint8)
+    roots[:, 0] = 1
+    roots[:, 1] = np.arange(B)
+    pool = [r for r in roots]
+    while len(pool) < n_data:
+        chosen = pool[int(np.random.choice(len(pool)))]
+        for _ in range(n_per_step):
+            if len(pool) < n_data:
+                k = int(np.random.choice(int(num_neighbours(chosen[None, :], B)[0])))
+                pool.append(neighbour_at_index_host(chosen, k, B))
+    return np.stack(pool[: max(n_data, B)])
+
+
+@pytest.mark.parametrize("gen,d", [("CKSHighDimSearchSpace", 5), ("CKSWithRQSearchSpace", 2), ("CKSWithRQSearchSpace", 1)])
+def test_native_producers_replay_numpy_choice(gen, d):
+    """C-ABI bosot_host_recursive_dataset / bosot_host_choices draw what one np.random.choice call per draw would have
+    drawn -- same records, same indices -- and leave NumPy's global generator in the same state."""
+    from bosot_b200.flat_search import legacy_choices
+
+    gram = Grammar.get(gen, d)
+    g = FlatCandidateGenerator(gram)
+    for n_data, per in ((1, 1), (gram.n_symbols, 1), (gram.n_symbols + 1, 1), (400, 1), (401, 3), (2500, 1)):
+        np.random.seed(100 + n_data)
+        ref = _python_recursive_dataset(gram, n_data, per)
+        ref_next = np.random.randint(0, 2**32, dtype=np.uint32)
+        np.random.seed(100 + n_data)
+        got = g.get_dataset_recursivly_generated(n_data, per)
+        assert np.array_equal(got, ref) and np.random.randint(0, 2**32, dtype=np.uint32) == ref_next
+    sizes = np.concatenate([np.ones(5, dtype=np.int64), np.random.default_rng(0).integers(1, 4000, 3000), [2**31, 2**32 - 1, 2**32]])
+    np.random.seed(3)
+    ref = np.array([int(np.random.choice(int(n))) for n in sizes])
+    ref_next = np.random.randint(0, 2**32, dtype=np.uint32)
+    np.random.seed(3)
+    got = legacy_choices(sizes)
+    assert np.array_equal(got, ref) and np.random.randint(0, 2**32, dtype=np.uint32) == ref_next
+    # offspring draws of the flat EA: survivor-major, one draw per offspring
+    surv = _python_recursive_dataset(gram, 300)
+    np.random.seed(4)
+    cnt = num_neighbours(surv, gram.n_symbols)
+    ref = np.array([int(np.random.choice(int(cnt[p]))) for p in np.repeat(np.arange(300), 4)])
+    np.random.seed(4)
+    parent, index = g.draw_offspring_indices(surv, 4)
+    assert np.array_equal(index, ref) and np.array_equal(parent, np.repeat(np.arange(300), 4))
+
+
 @pytest.mark.gpu
 def test_device_moves_match_host():
     torch = pytest.importorskip("torch")
