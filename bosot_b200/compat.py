@@ -4,6 +4,8 @@ The mirror keeps the reference's module paths (``bosot.kernels.kernel_kernel_gra
 ``bosot.models.object_gp_model``, ``bosot.bayesian_optimization.bayesian_optimizer_objects`` ...),
 so existing scripts only need this one call before their imports."""
 import importlib
+import importlib.abc
+import importlib.util
 import sys
 
 _MODULES = [
@@ -27,11 +29,35 @@ _MODULES = [
 ]
 
 
+class _AliasFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """``bosot.<anything>`` -> the module object of ``bosot_b200.<anything>`` (never a second copy of a module:
+    ``isinstance`` checks in the factories compare classes by identity)."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname != "bosot" and not fullname.startswith("bosot."):
+            return None
+        real = "bosot_b200" + fullname[len("bosot"):]
+        try:
+            if importlib.util.find_spec(real) is None:
+                return None
+        except (ImportError, ValueError):
+            return None
+        return importlib.util.spec_from_loader(fullname, self)
+
+    def create_module(self, spec):
+        return importlib.import_module("bosot_b200" + spec.name[len("bosot"):])
+
+    def exec_module(self, module):  # already executed under its real name
+        pass
+
+
 def install_as_bosot() -> None:
     if "bosot" in sys.modules and not getattr(sys.modules["bosot"], "__bosot_b200_alias__", False):
         raise RuntimeError("a different `bosot` package is already imported")
     root = importlib.import_module("bosot_b200")
     root.__bosot_b200_alias__ = True
     sys.modules["bosot"] = root
+    if not any(isinstance(f, _AliasFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _AliasFinder())
     for name in _MODULES:
         sys.modules["bosot." + name] = importlib.import_module("bosot_b200." + name)

@@ -1,3 +1,4 @@
+import os
 """CPU: the host-side mirror of the reference API (expression trees, search spaces, candidate
 generators, configs / factories).  The golden fixtures hold trees produced by the REFERENCE's own
 generators under fixed np.random seeds, so reproducing their name strings pins enumeration order
@@ -119,3 +120,32 @@ def test_configs_behave_like_settings_objects():
         CKSWithRQGeneratorConfig()  # input_dimension is required
     with pytest.raises(TypeError):
         CKSWithRQGeneratorConfig(input_dimension=1, bogus=2)
+
+
+def test_bosot_alias_never_imports_a_module_twice():
+    """``import bosot.<anything>`` after ``install_as_bosot()`` yields THE module object of ``bosot_b200.<anything>``,
+    also for modules outside the explicit alias list: the factories dispatch with isinstance, so a second copy of a
+    config module would break them."""
+    import importlib
+    import subprocess
+    import sys
+
+    code = (
+        "import bosot_b200.compat as c; c.install_as_bosot()\n"
+        "import importlib\n"
+        "names = ['configs.kernels.kernel_grammar_generators.generator_configs', 'oracles.structural_oracle',\n"
+        "         'kernels.kernel_kernel_hellinger', 'configs.kernels.hellinger_kernel_kernel_configs', 'flat_search']\n"
+        "for n in names:\n"
+        "    assert importlib.import_module('bosot.' + n) is importlib.import_module('bosot_b200.' + n), n\n"
+        "from bosot.configs.kernels.kernel_grammar_generators.generator_configs import CKSHighDimGeneratorConfig\n"
+        "from bosot.kernels.kernel_grammar.generator_factory import GeneratorFactory\n"
+        "assert type(GeneratorFactory.build(CKSHighDimGeneratorConfig(input_dimension=3))).__name__ == 'KernelGrammarCandidateGenerator'\n"
+        "try:\n"
+        "    import bosot.no_such_module\n"
+        "    raise SystemExit(2)\n"
+        "except ImportError:\n"
+        "    pass\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
