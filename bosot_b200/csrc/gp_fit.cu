@@ -7,7 +7,8 @@
 //     dloss/dtheta = 0.5 * sum_ij (Kinv_ij - alpha_i alpha_j) dK_ij/dtheta,  alpha = K^-1 r
 // The three E x E per-feature distance matrices Df are constants of the fit (they come from the pair
 // kernel once per model update), E is small (tens to ~150), so the whole evaluation is one CTA:
-// Cholesky in shared memory, two triangular solves, L^-1 written into the unused upper triangle,
+// Cholesky in shared memory fused with the inversion of the factor (one sweep of E steps, one barrier each,
+// L^-1 written into the unused upper triangle), alpha from two triangular matrix-vector products,
 // and Kinv_ij formed on the fly as row dot products while the five weighted sums are accumulated.
 // Gradients are returned with respect to the CONSTRAINED quantities (w_f treated as independent, ls,
 // var, noise, c); the host applies the chain rule of the sigmoid / softplus transforms.
@@ -17,7 +18,8 @@
 
 namespace bosot {
 
-constexpr int kFitThreads = 256;
+// one CTA of TILE x TILE threads: 16 x 16 up to 48 evaluated kernels, 32 x 32 beyond (measured: at E = 26 / 80 / 160 the
+// small tile takes 21 / 106 / 473 us, the large one 25 / 85 / 313 us)
 constexpr int kFitMaxE = 160;
 
 struct FitParams {
@@ -29,6 +31,7 @@ struct FitParams {
   double* out;       // [0] loss, [1..3] dL/dw_f, [4] dL/dls, [5] dL/dvar, [6] dL/dnoise, [7] dL/dc, [8] info (0 ok, k+1 = minor k not PD)
 };
 
+template <int kFitThreads>
 __device__ __forceinline__ double block_sum(double v, double* red) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   __syncthreads();
@@ -39,54 +42,63 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return s;
 }
 
-__global__ void __launch_bounds__(kFitThreads)
+template <int kFitTile>
+__global__ void __launch_bounds__(kFitTile * kFitTile)
 gp_nll_grad_kernel(FitParams p) {
+  constexpr int kFitThreads = kFitTile * kFitTile;
   extern __shared__ __align__(16) uint8_t smem[];
   const int E = p.E, lda = E | 1;
   double* A = reinterpret_cast<double*>(smem);  // [E][lda]: lower = L, strict upper = (L^-1)^T
   double* r = A + (size_t)E * lda;              // residual, then forward-solve result
   double* alpha = r + E;
   double* dinv = alpha + E;                     // diagonal of L^-1
-  double* red = dinv + E;                       // [8]
+  double* red = dinv + E;                       // [kFitThreads / 32]
   __shared__ int s_info;
   const int tid = threadIdx.x;
   const double inv_ls2 = 1.0 / (p.ls * p.ls);
   const size_t plane = (size_t)E * p.ld;
   if (tid == 0) s_info = 0;
 
-  // K (lower triangle) and the residual
-  for (int idx = tid; idx < E * E; idx += kFitThreads) {
-    const int i = idx / E, j = idx - i * E;
-    if (j <= i) {
-      const size_t o = (size_t)i * p.ld + j;
-      const double D = p.w[0] * p.Df[o] + p.w[1] * p.Df[plane + o] + p.w[2] * p.Df[2 * plane + o];
-      A[i * lda + j] = p.var * exp(-D * inv_ls2) + (i == j ? p.noise : 0.0);
+  // K (lower triangle incl. diagonal), Y = 0 in the strict upper triangle, and the residual
+  const int tx = tid & (kFitTile - 1), ty = tid / kFitTile;  // thread tile of the two-dimensional sweeps
+  for (int i = ty; i < E; i += kFitTile) {
+    for (int j = tx; j < E; j += kFitTile) {
+      double v = 0.0;
+      if (j <= i) {
+        const size_t o = (size_t)i * p.ld + j;
+        const double D = p.w[0] * p.Df[o] + p.w[1] * p.Df[plane + o] + p.w[2] * p.Df[2 * plane + o];
+        v = p.var * exp(-D * inv_ls2) + (i == j ? p.noise : 0.0);
+      }
+      A[i * lda + j] = v;
     }
   }
   for (int i = tid; i < E; i += kFitThreads) r[i] = p.y[i] - p.c;
   __syncthreads();
 
-  // Cholesky, right-looking
+  // ONE sweep of E steps, one barrier each, factorises K and inverts the factor.  Step k reads the pivot
+  // d_k = A[k][k] and the (unscaled) column k of the lower triangle -- neither is touched again -- and applies
+  //   (a) the trailing Cholesky update        A[i][j] -= A[i][k] A[j][k] / d_k            k < j <= i
+  //   (b) the forward substitution of L Y = I  Y[i][j] -= A[i][k] Y[k][j] / d_k           j <= k < i, Y[k][k] = 1
+  // with Y[i][j] (i > j) kept transposed in the strict upper triangle, A[j][i].  In scaled terms L[i][k] =
+  // A[i][k] / sqrt(d_k) and L^-1[i][j] = Y[i][j] / sqrt(d_i): no thread ever waits for one that takes a square root.
   for (int k = 0; k < E; ++k) {
-    if (tid == 0) {
-      const double a = A[k * lda + k];
-      if (!(a > 0.0) && s_info == 0) s_info = k + 1;
-      A[k * lda + k] = sqrt(a);
+    const double dk = A[k * lda + k];
+    if (!(dk > 0.0)) {  // uniform: every thread reads the same value
+      if (tid == 0) s_info = k + 1;
+      break;
     }
-    __syncthreads();
-    const double piv = A[k * lda + k];
-    for (int i = k + 1 + tid; i < E; i += kFitThreads) A[i * lda + k] /= piv;
-    __syncthreads();
-    const int n = E - k - 1;
-    for (int idx = tid; idx < n * n; idx += kFitThreads) {
-      const int a = idx / n, b = idx - a * n;
-      if (b <= a) {
-        const int i = k + 1 + a, j = k + 1 + b;
-        A[i * lda + j] -= A[i * lda + k] * A[j * lda + k];
-      }
+    const double inv = 1.0 / dk;
+    for (int i = k + 1 + ty; i < E; i += kFitTile) {
+      const double lik = A[i * lda + k] * inv;
+      for (int j = k + 1 + tx; j <= i; j += kFitTile) A[i * lda + j] -= lik * A[j * lda + k];
+    }
+    for (int j = ty; j <= k; j += kFitTile) {
+      const double c = (j == k ? 1.0 : A[j * lda + k]) * inv;
+      for (int i = k + 1 + tx; i < E; i += kFitTile) A[j * lda + i] -= A[i * lda + k] * c;
     }
     __syncthreads();
   }
+  __syncthreads();
   if (s_info != 0) {  // not positive definite: report like a failed Cholesky, the caller retries
     if (tid == 0) {
       const double qnan = __longlong_as_double(0x7ff8000000000000LL);
@@ -95,39 +107,34 @@ gp_nll_grad_kernel(FitParams p) {
     }
     return;
   }
-
-  // alpha = K^-1 r : forward then backward substitution (column sweeps)
-  for (int k = 0; k < E; ++k) {
-    if (tid == 0) r[k] /= A[k * lda + k];
-    __syncthreads();
-    const double zk = r[k];
-    for (int i = k + 1 + tid; i < E; i += kFitThreads) r[i] -= A[i * lda + k] * zk;
-    __syncthreads();
+  double logdet = 0.0;
+  for (int k = tid; k < E; k += kFitThreads) {
+    const double dk = A[k * lda + k];
+    dinv[k] = 1.0 / sqrt(dk);  // diagonal of L^-1
+    logdet += 0.5 * log(dk);   // log L[k][k]
   }
-  double quad = 0.0, logdet = 0.0;
-  for (int i = tid; i < E; i += kFitThreads) { quad += r[i] * r[i]; logdet += log(A[i * lda + i]); }
-  quad = block_sum(quad, red);
-  logdet = block_sum(logdet, red);
-  for (int i = tid; i < E; i += kFitThreads) alpha[i] = r[i];
+  logdet = block_sum<kFitThreads>(logdet, red);  // (two barriers: dinv is visible afterwards)
+  // strict upper triangle: A[j][i] = L^-1[i][j] = Y[i][j] / L[i][i], i > j
+  for (int j = ty; j < E; j += kFitTile)
+    for (int i = j + 1 + tx; i < E; i += kFitTile) A[j * lda + i] *= dinv[i];
   __syncthreads();
-  for (int k = E - 1; k >= 0; --k) {
-    if (tid == 0) alpha[k] /= A[k * lda + k];
-    __syncthreads();
-    const double ak = alpha[k];
-    for (int i = tid; i < k; i += kFitThreads) alpha[i] -= A[k * lda + i] * ak;
-    __syncthreads();
+  // alpha = K^-1 r = L^-T (L^-1 r): two triangular matrix-vector products, no sequential substitution
+  for (int i = tid; i < E; i += kFitThreads) {
+    double z = dinv[i] * r[i];
+    for (int j = 0; j < i; ++j) z += A[j * lda + i] * r[j];
+    alpha[i] = z;  // z = L^-1 r, kept in alpha's storage until the second product
   }
-
-  // L^-1, one thread per column j, written transposed into the strict upper triangle: A[j][i] = Linv[i][j], i > j
+  __syncthreads();
+  double quad = 0.0;
+  for (int i = tid; i < E; i += kFitThreads) quad += alpha[i] * alpha[i];
+  quad = block_sum<kFitThreads>(quad, red);
   for (int j = tid; j < E; j += kFitThreads) {
-    const double dj = 1.0 / A[j * lda + j];
-    dinv[j] = dj;
-    for (int i = j + 1; i < E; ++i) {
-      double s = A[i * lda + j] * dj;  // k = j term
-      for (int k = j + 1; k < i; ++k) s += A[i * lda + k] * A[j * lda + k];
-      A[j * lda + i] = -s / A[i * lda + i];
-    }
+    double a = dinv[j] * alpha[j];
+    for (int i = j + 1; i < E; ++i) a += A[j * lda + i] * alpha[i];
+    r[j] = a;
   }
+  __syncthreads();
+  for (int j = tid; j < E; j += kFitThreads) alpha[j] = r[j];
   __syncthreads();
 
   // Kinv_ij = sum_{k >= i} U[i][k] U[j][k] (i >= j), U = (L^-1)^T upper triangular (diag in dinv); weighted sums
@@ -154,14 +161,14 @@ gp_nll_grad_kernel(FitParams p) {
     s_f2 += qg * d2;
     if (i == j) s_noise += q;
   }
-  s_var = block_sum(s_var, red);
-  s_f0 = block_sum(s_f0, red);
-  s_f1 = block_sum(s_f1, red);
-  s_f2 = block_sum(s_f2, red);
-  s_noise = block_sum(s_noise, red);
+  s_var = block_sum<kFitThreads>(s_var, red);
+  s_f0 = block_sum<kFitThreads>(s_f0, red);
+  s_f1 = block_sum<kFitThreads>(s_f1, red);
+  s_f2 = block_sum<kFitThreads>(s_f2, red);
+  s_noise = block_sum<kFitThreads>(s_noise, red);
   double s_alpha = 0.0;
   for (int i = tid; i < E; i += kFitThreads) s_alpha += alpha[i];
-  s_alpha = block_sum(s_alpha, red);
+  s_alpha = block_sum<kFitThreads>(s_alpha, red);
 
   if (tid == 0) {
     p.out[0] = 0.5 * quad + logdet + 0.5 * E * 1.8378770664093454836;  // log(2 pi)
@@ -191,15 +198,18 @@ extern "C" int bosot_gp_nll_grad(const double* d_Df, int n_eval, int64_t ld, con
   p.Df = d_Df; p.E = n_eval; p.ld = ld; p.y = d_y;
   p.w[0] = weights[0]; p.w[1] = weights[1]; p.w[2] = weights[2];
   p.ls = lengthscale; p.var = variance; p.noise = noise_variance; p.c = mean_c; p.out = d_out9;
-  const size_t smem = sizeof(double) * ((size_t)n_eval * (n_eval | 1) + 3 * (size_t)n_eval + 8);
+  const size_t smem = sizeof(double) * ((size_t)n_eval * (n_eval | 1) + 3 * (size_t)n_eval + 32);
   static std::atomic<bool> attr_set[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
   int dev = 0;
   cudaGetDevice(&dev);
   if (!(dev < 64 && attr_set[dev])) {
-    if (int rc = cuda_check(cudaFuncSetAttribute(gp_nll_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024),
-                            "cudaFuncSetAttribute(gp_nll_grad_kernel)")) return rc;
+    if (int rc = cuda_check(cudaFuncSetAttribute(gp_nll_grad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024),
+                            "cudaFuncSetAttribute(gp_nll_grad_kernel<16>)")) return rc;
+    if (int rc = cuda_check(cudaFuncSetAttribute(gp_nll_grad_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024),
+                            "cudaFuncSetAttribute(gp_nll_grad_kernel<32>)")) return rc;
     if (dev < 64) attr_set[dev] = true;
   }
-  gp_nll_grad_kernel<<<1, kFitThreads, smem, (cudaStream_t)stream>>>(p);
+  if (n_eval <= 48) gp_nll_grad_kernel<16><<<1, 256, smem, (cudaStream_t)stream>>>(p);
+  else gp_nll_grad_kernel<32><<<1, 1024, smem, (cudaStream_t)stream>>>(p);
   return after_launch("gp_nll_grad_kernel");
 }
