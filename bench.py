@@ -328,6 +328,52 @@ def main() -> None:
                   ei_candidates_per_s=C4_POOL / (ms4 * 1e-3), e2e_ms=ms4_e2e, e2e_pairs_per_s=C4_POOL * C4_EVAL / (ms4_e2e * 1e-3),
                   e2e_ei_candidates_per_s=C4_POOL / (ms4_e2e * 1e-3))
 
+    # One BO loop at the shape of BASELINE.json config 4 (Airfoil-shaped: CKSHighDim d = 5, 10k-candidate EA pool per step)
+    # through the reference-facing API: model update (ML-II fit on the device) + EA acquisition optimisation per BO step;
+    # a deterministic structural objective stands in for the reference's model-evidence oracle (out of scope).
+    bo_loop = {}
+    if rank == 0 and world == 1:
+        try:
+            import time as _time
+
+            from bosot_b200.bayesian_optimization.bayesian_optimizer_objects import BayesianOptimizerObjects
+            from bosot_b200.configs.bayesian_optimization.bayesian_optimizer_objects_configs import ObjectBOExpectedImprovementEAConfig
+            from bosot_b200.configs.kernels.grammar_tree_kernel_kernel_configs import OTWeightedDimsExtendedGrammarKernelConfig
+            from bosot_b200.configs.kernels.kernel_grammar_generators.generator_configs import CKSHighDimGeneratorConfig
+            from bosot_b200.configs.models.object_gp_model_config import BasicObjectGPModelConfig
+            from bosot_b200.kernels.kernel_grammar.generator_factory import GeneratorFactory
+            from bosot_b200.models.gp_model import PredictionQuantity
+            from bosot_b200.models.model_factory import ModelFactory
+            from bosot_b200.models.object_mean_functions import ObjectConstant
+            from bosot_b200.oracles.structural_oracle import StructuralOracle
+
+            state = np.random.get_state()
+            np.random.seed(0)
+            gen_bo = GeneratorFactory.build(CKSHighDimGeneratorConfig(input_dimension=DIM))
+            roots = [str(r) for r in gen_bo.search_space.get_root_expressions()]
+            model_bo = ModelFactory.build(BasicObjectGPModelConfig(kernel_config=OTWeightedDimsExtendedGrammarKernelConfig(input_dimension=DIM),
+                                                                   prediction_quantity=PredictionQuantity.PREDICT_F,
+                                                                   perform_multi_start_optimization=False))
+            model_bo.set_mean_function(ObjectConstant())
+            bo = BayesianOptimizerObjects(**ObjectBOExpectedImprovementEAConfig(n_steps_evolutionary=3, population_evolutionary=C4_POOL).dict())
+            bo.set_model(model_bo)
+            bo.set_oracle(StructuralOracle(roots, seed=7, noise=0.01))
+            bo.set_candidate_generator(gen_bo)
+            bo.sample_train_set(3 * len(roots))
+            bo.maximize(2)  # warm-up
+            torch.cuda.synchronize(dev)
+            t0 = _time.perf_counter()
+            n_bo = 10
+            bo.maximize(n_bo)
+            torch.cuda.synchronize(dev)
+            bo_loop = dict(workload="c4_airfoil_shape_bo_loop: CKSHighDim d=5, EI + EA with a 10k-candidate pool x 3 generations per step, "
+                                    "E = %d..%d evaluated kernels" % (3 * len(roots) + 2, 3 * len(roots) + 2 + n_bo),
+                           ms_per_bo_step=1e3 * (_time.perf_counter() - t0) / n_bo, bo_steps=n_bo,
+                           ei_evaluations_per_step=3 * C4_POOL, objective="structural oracle (the reference's evidence oracle is out of scope)")
+            np.random.set_state(state)
+        except Exception as exc:  # the extras never break the headline line
+            bo_loop = dict(error="%s: %s" % (type(exc).__name__, exc))
+
     # Hellinger kernel-kernel at the same 10k x 50 shape: S = 100 hyper-parameter samples, V = 20 virtual points
     hell = {}
     if rank == 0:
@@ -444,6 +490,7 @@ def main() -> None:
             cpu_baseline=cpu,
             c4_10k_x_50=c4,
             hellinger_10k_x_50=hell,
+            bo_loop_c4=bo_loop,
         )
         print(json.dumps(line), flush=True)
     if world > 1:
