@@ -86,6 +86,54 @@ def test_native_producers_replay_numpy_choice(gen, d):
     assert np.array_equal(index, ref) and np.array_equal(parent, np.repeat(np.arange(300), 4))
 
 
+def test_native_producers_error_behaviour():
+    """Return codes of the host entry points: BOSOT_ERAW when the block of raw outputs is too short (the wrapper then
+    retries with a longer block and still leaves the generator where the reference would), BOSOT_EINVAL on bad sizes,
+    BOSOT_ETREE when a move would exceed the 63-node record."""
+    import ctypes as C
+
+    from bosot_b200 import _lib
+    from bosot_b200.flat_search import _replay_global_rng
+
+    lib = _lib.load()
+    raw = np.arange(1, dtype=np.uint32)
+    sizes = np.full(8, 1000, dtype=np.int64)
+    out = np.empty(8, dtype=np.int64)
+    used = C.c_int64(0)
+    assert lib.bosot_host_choices(raw.ctypes.data, 1, sizes.ctypes.data, 8, out.ctypes.data, C.byref(used)) == _lib.ERAW
+    bad = np.zeros(1, dtype=np.int64)
+    assert lib.bosot_host_choices(raw.ctypes.data, 1, bad.ctypes.data, 1, out.ctypes.data, C.byref(used)) == -1  # BOSOT_EINVAL
+    # the wrapper grows the block: start far too small on purpose
+    sizes = np.random.default_rng(1).integers(2, 5000, 4000)
+    np.random.seed(8)
+    ref = np.array([int(np.random.choice(int(n))) for n in sizes])
+    ref_next = np.random.randint(0, 2**32, dtype=np.uint32)
+    np.random.seed(8)
+    got = np.empty(len(sizes), dtype=np.int64)
+    sz = np.ascontiguousarray(sizes, dtype=np.int64)
+    _replay_global_rng(lambda r, n, u: lib.bosot_host_choices(r, n, sz.ctypes.data, len(sz), got.ctypes.data, u), 1)
+    assert np.array_equal(got, ref) and np.random.randint(0, 2**32, dtype=np.uint32) == ref_next
+    pool = np.empty((64, 64), dtype=np.uint8)
+    raw = np.zeros(16, dtype=np.uint32)
+    assert lib.bosot_host_recursive_dataset(raw.ctypes.data, len(raw), 1, -5, 1, pool.ctypes.data, C.byref(used)) == -1
+    # a walk that outgrows the record: always take the newest element and its last neighbour (an extension, +2 nodes);
+    # a raw output equal to n - 1 is accepted at once, so the stream can be written down in advance
+    B, raw, grown = 3, [], [np.array([1, 0] + [0xFF] * 62, dtype=np.uint8)]
+    n_pool = B
+    for _ in range(40):
+        raw.append(n_pool - 1)  # choice(len(pool)) -> the newest element (the first pick is root B - 1: same size as root 0)
+        count = int(num_neighbours(grown[-1][None, :], B)[0])
+        raw.append(count - 1)
+        if grown[-1][0] + 2 > 63:
+            break
+        grown.append(neighbour_at_index_host(grown[-1], count - 1, B))
+        n_pool += 1
+    raw = np.array(raw, dtype=np.uint32)
+    pool = np.empty((200, 64), dtype=np.uint8)
+    assert lib.bosot_host_recursive_dataset(raw.ctypes.data, len(raw), B, 200, 1, pool.ctypes.data, C.byref(used)) == -3  # BOSOT_ETREE
+    assert b"63-node" in lib.bosot_last_error()
+
+
 @pytest.mark.gpu
 def test_device_moves_match_host():
     torch = pytest.importorskip("torch")
