@@ -454,6 +454,20 @@ def main() -> None:
                                      "K_diag taken as variance" % (sample4, C4_EVAL, r4["seconds"], r4["cores"]),
                               gpu_matches_cpu_on_sample=ok4)
         c4["e2e_speedup_vs_cpu_port"] = c4["e2e_ei_candidates_per_s"] / r4["cand_per_s"]
+        # the reference AS SHIPPED, at its own size: one acquisition_function call on an EA generation of 100 candidates,
+        # one process, K_diag through the full N x N x F tensor (kernel_kernel_grammar_tree.py:115-119; SURVEY.md 8d plan 1)
+        from oracle import ref_numpy as rn_
+
+        sym4 = rn_.base_kernel_names(GEN, DIM)
+        ev_t = [cpu_baseline._decode(r_, sym4) for r_ in ev4]
+        ca_t = [cpu_baseline._decode(r_, sym4) for r_ in ca4[:100]]
+        t_lit = []
+        for _ in range(3):
+            t0_ = time.perf_counter()
+            lit = rn_.acquisition_function(ev_t, y4, ca_t, rn_.Hyper(**H1), GEN, DIM, literal_kdiag=True)
+            t_lit.append(time.perf_counter() - t0_)
+        c4["cpu_port"]["literal_call_100_candidates_ms"] = 1e3 * float(np.median(t_lit))
+        c4["cpu_port"]["literal_call_matches_gpu"] = bool(np.allclose(o4[2][:100].cpu().numpy(), lit["acq"], rtol=1e-6, atol=1e-12))
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
