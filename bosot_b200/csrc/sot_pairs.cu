@@ -140,9 +140,38 @@ scan_kernel(const uint8_t* __restrict__ trees, int64_t n_trees, int n_symbols, u
     dst[1] = make_uint2(v.z, v.w);
   }
   __syncthreads();
+  // Threads of a warp run their trees in lock step (the passes of scan_tree are branch-free per token), so a warp
+  // costs as much as its LONGEST tree: hand the trees out sorted by token count (counting sort over the CTA's
+  // records) and every warp gets trees of similar length.
+  __shared__ int bin_pos[64];
+  __shared__ uint8_t order[kScanThreads];
+  if (threadIdx.x < 64) bin_pos[threadIdx.x] = 0;
+  __syncthreads();
+  int my_bin = 0;
   if ((int)threadIdx.x < in_block) {
-    const int st = scan_tree(smem + threadIdx.x * kRecBytes, n_symbols);
-    if (status) status[base + threadIdx.x] = st;
+    const int n = smem[threadIdx.x * kRecBytes + kRecTok];
+    my_bin = n < 64 ? n : 0;  // malformed lengths fail fast in scan_tree
+    atomicAdd(&bin_pos[my_bin], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {  // exclusive scan of the 64 bin counts: two bins per lane
+    const int a = bin_pos[2 * threadIdx.x], b = bin_pos[2 * threadIdx.x + 1];
+    int inc = a + b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((int)threadIdx.x >= o) inc += v;
+    }
+    bin_pos[2 * threadIdx.x] = inc - a - b;
+    bin_pos[2 * threadIdx.x + 1] = inc - b;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < in_block) order[atomicAdd(&bin_pos[my_bin], 1)] = (uint8_t)threadIdx.x;
+  __syncthreads();
+  if ((int)threadIdx.x < in_block) {
+    const int mine = order[threadIdx.x];
+    const int st = scan_tree(smem + mine * kRecBytes, n_symbols);
+    if (status) status[base + mine] = st;
   }
   __syncthreads();
   // coalesced copy-out of the compact part (320 B = 40 x 8 B per record)
