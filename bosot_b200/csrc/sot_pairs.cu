@@ -309,6 +309,8 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   const bool use_states = meta->use_states != 0;
   const int n_flat = meta->n_flat;
 
+#pragma unroll 1
+  for (int e = 2 * lane; e < e_pad; e += 64) *reinterpret_cast<uint2*>(acc + e) = make_uint2(0u, 0u);
   for (; t < p.n_cand; t += stride) {
     const Slice cur = nxt;
     if (t + stride < p.n_cand) nxt = load_slice(t + stride);  // prefetch behind this tree's work
@@ -328,9 +330,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
       continue;
     }
 
-    __syncwarp();
-#pragma unroll 1
-    for (int e = 2 * lane; e < e_pad; e += 64) *reinterpret_cast<uint2*>(acc + e) = make_uint2(0u, 0u);
+    __syncwarp();  // acc[] is all zero here: zeroed before the loop, and every entry is cleared again by the epilogue that reads it
 #pragma unroll 1
     for (int s = lane; s < BOSOT_MAX_SYMBOLS + BOSOT_MAX_BLOCKS; s += 32) scnt[s] = 0u;
     __syncwarp();
@@ -456,8 +456,8 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
         for (unsigned todo = sym_leads; todo;) {
           const int src = __ffs(todo) - 1;
           todo &= todo - 1;
-          const uint32_t s = __shfl_sync(full, sym, src);
-          const uint32_t ca = __shfl_sync(full, cnt_sym, src);
+          const uint32_t sc = __shfl_sync(full, sym | (cnt_sym << 8), src);  // symbol < 64, count <= 32
+          const uint32_t s = sc & 0xffu, ca = sc >> 8;
           const uint32_t* col = symT2 + s * (uint32_t)half_pad + wb;
 #pragma unroll
           for (int q = 0; q < RP; ++q) msub2[q] += __vminu2(ca * tb2[q], col[32 * q] * (uint32_t)nn);
@@ -490,7 +490,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
         }
       }
       // epilogue in groups of up to 4 trees per lane: distances, weighted sum, Gram entry
-      const uint32_t* accp = acc + eb;
+      uint32_t* accp = acc + eb;
       const uint8_t* nnp = e_nn + eb;
       const uint8_t* nlp = e_nl + eb;
       const double* rsp = e_rsub + eb;
@@ -504,6 +504,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
           const int r = r0 + i;
           if (r < R) {
             const uint32_t a = accp[32 * r];
+            accp[32 * r] = 0u;  // ready for the next candidate
             const uint32_t m_sub = ((msub2[r >> 1] >> (16 * (r & 1))) & 0xffffu) + (a & 0xffffu), m_path = a >> 16;
             const uint32_t tb_sub = nnp[32 * r], tb_path = nlp[32 * r];
             // L1 = 2 - 2 M / (Ta Tb) = 2 (Ta Tb - M) / (Ta Tb) with the integer difference formed first: exactly 0
