@@ -30,6 +30,7 @@
 //                                      The next tree's record is prefetched into registers while the
 //                                      current one is processed.
 #include <atomic>
+#include <mutex>
 #include "sot_common.cuh"
 #include "launch.cuh"
 #include "fast_math.cuh"
@@ -54,6 +55,7 @@ struct PairParams {
   double* Df;
   int64_t ld;
   const uint8_t* recs;  // compact records written by scan_kernel: [n_cand][kScanBytes]
+  unsigned long long* next;  // work counter (zeroed by the scan launch): the warps claim candidates one at a time
 };
 
 // per-warp shared memory: candidate dim-wise vector, block-state distance table, walk segments, accumulators, symbol counts
@@ -129,8 +131,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---- launch 1: thread-per-tree scan -> compact records ------------------------------------
 __global__ void __launch_bounds__(kScanThreads)
 scan_kernel(const uint8_t* __restrict__ trees, int64_t n_trees, int n_symbols, uint8_t* __restrict__ recs_out,
-            int32_t* __restrict__ status) {
+            int32_t* __restrict__ status, unsigned long long* __restrict__ next) {
   extern __shared__ __align__(16) uint8_t smem[];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *next = 0ULL;  // work counter of the pair launch that follows on the stream
   const int64_t base = (int64_t)blockIdx.x * kScanThreads;
   const int in_block = (int)min((int64_t)kScanThreads, n_trees - base);
   for (int w = threadIdx.x; w < in_block * 4; w += kScanThreads) {  // coalesced: 16 B per thread
@@ -301,8 +304,15 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     return s;
   };
 
-  const int64_t stride = (int64_t)gridDim.x * n_warps;
-  int64_t t = (int64_t)blockIdx.x * n_warps + warp;
+  // Candidates are claimed one at a time from a global counter, one claim ahead of the work: trees differ in cost by an
+  // order of magnitude (1 .. 63 nodes), and with a static stride the warp with the unluckiest share decided when the
+  // kernel ended (about 240 candidates per warp at 1 M, 30 at 125 k per GPU).
+  auto claim = [&]() {
+    unsigned long long v = 0ULL;
+    if (lane == 0) v = atomicAdd(p.next, 1ULL);
+    return (int64_t)__shfl_sync(full, v, 0);
+  };
+  int64_t t = claim();
   Slice nxt;
   if (t < p.n_cand) nxt = load_slice(t);
   mbar_wait(bar, 0);  // tables landed (the copy overlapped the first record load)
@@ -311,9 +321,10 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
 
 #pragma unroll 1
   for (int e = 2 * lane; e < e_pad; e += 64) *reinterpret_cast<uint2*>(acc + e) = make_uint2(0u, 0u);
-  for (; t < p.n_cand; t += stride) {
+  for (int64_t t_next; t < p.n_cand; t = t_next) {
     const Slice cur = nxt;
-    if (t + stride < p.n_cand) nxt = load_slice(t + stride);  // prefetch behind this tree's work
+    t_next = claim();
+    if (t_next < p.n_cand) nxt = load_slice(t_next);  // prefetch behind this tree's work
 
     const int nn = cur.meta & 0xff, nl = (cur.meta >> 8) & 0xff, ni = (cur.meta >> 16) & 0xff;
     const bool bad = (cur.meta >> 24) != 0;
@@ -565,6 +576,27 @@ static int ensure_recip_table() {
   return BOSOT_OK;
 }
 
+// Work counters of the pair launches: a small per-device ring in global memory (allocated once, never freed); every
+// bosot_sot_pairs call takes the next one, its scan launch zeroes it.  64 calls may be in flight per device.
+constexpr int kCounterRing = 64;
+static unsigned long long* g_counters[64] = {nullptr};
+static std::atomic<unsigned> g_counter_seq[64];
+static std::mutex g_counter_mutex;
+
+static int next_counter(int dev, unsigned long long** out) {
+  if (dev < 0 || dev >= 64) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: device index out of range");
+  if (!g_counters[dev]) {
+    std::lock_guard<std::mutex> lock(g_counter_mutex);
+    if (!g_counters[dev]) {
+      void* ptr = nullptr;
+      if (int rc = cuda_check(cudaMalloc(&ptr, sizeof(unsigned long long) * kCounterRing), "cudaMalloc(work counters)")) return rc;
+      g_counters[dev] = static_cast<unsigned long long*>(ptr);
+    }
+  }
+  *out = g_counters[dev] + (g_counter_seq[dev].fetch_add(1u) % kCounterRing);
+  return BOSOT_OK;
+}
+
 size_t pairs_scratch_bytes(int64_t n_cand) { return align16((size_t)n_cand * kScanBytes); }
 
 int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar, const void* d_eval_blob,
@@ -609,8 +641,9 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   }
   const int64_t scan_blocks = (n_cand + kScanThreads - 1) / kScanThreads;
   if (scan_blocks > 0x7fffffffLL) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: too many candidates");
+  if (int rc = next_counter(dev, &p.next)) return rc;
   scan_kernel<<<(unsigned)scan_blocks, kScanThreads, kScanThreads * kRecBytes, stream>>>(
-      d_trees, n_cand, grammar->n_symbols, static_cast<uint8_t*>(d_scratch), d_status);
+      d_trees, n_cand, grammar->n_symbols, static_cast<uint8_t*>(d_scratch), d_status, p.next);
   if (int rc = after_launch("scan_kernel")) return rc;
 
   // launch 2: pairs.  One persistent CTA per SM; small pools shrink the CTA so that every SM gets warps.
