@@ -8,11 +8,15 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "bosot_b200", "libbosot_b200.so")
+# kernel label -> substring of the mangled name (resolved against the symbols of the built library)
 KERNELS = {
-    "scan_kernel": "_ZN5bosot11scan_kernelEPKhliPhPi",
-    "sot_pair_kernel_R7": "_ZN5bosot15sot_pair_kernelILi7ELb0EEEvNS_10PairParamsE13bosot_grammar",
-    "posterior_ws_kernel_TC64": "_ZN5bosot19posterior_ws_kernelILi64EEEvNS_10PostParamsE",
+    "scan_kernel": "11scan_kernelE",
+    "sot_pair_kernel_R7": "15sot_pair_kernelILi7ELb0E",
+    "posterior_ws_kernel_TC64": "19posterior_ws_kernelILi64E",
 }
+_symbols = [l.split("Function :")[1].strip() for l in subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout.splitlines()
+            if "Function :" in l]
+KERNELS = {name: next(sym for sym in _symbols if part in sym) for name, part in KERNELS.items()}
 tag = sys.argv[1] if len(sys.argv) > 1 else "sass"
 for name, sym in KERNELS.items():
     out = subprocess.run(["cuobjdump", "-sass", "-fun", sym, LIB], capture_output=True, text=True).stdout
