@@ -40,6 +40,39 @@ def test_encode_roundtrip_names_tuples(golden):
     assert np.all(enc[:, 0] == [2 * rn.count_leaves(t) - 1 for t in tuples])
 
 
+def test_encode_roundtrip_random_trees_property():
+    """Property test (hypothesis): for random binary trees over every search space, record -> name -> record and
+    record -> tuple -> record are identities, the node-count byte is 2 * leaves - 1, and the oracle's own parser
+    agrees with the product's printer."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    spaces = [("CKSWithRQSearchSpace", 2), ("CKSHighDimSearchSpace", 5), ("CompositionalKernelSearchSpace", 3), ("NDimFullKernelsSearchSpace", 2)]
+
+    def trees(symbols):
+        leaf = st.sampled_from(symbols)
+        return st.recursive(leaf, lambda kids: st.tuples(st.sampled_from(["ADD", "MULTIPLY"]), kids, kids), max_leaves=32)
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.data())
+    def run(data):
+        gen, d = data.draw(st.sampled_from(spaces))
+        g = Grammar.get(gen, d)
+        t = data.draw(trees(g.symbols))
+        if rn.count_leaves(t) > 32:
+            with pytest.raises(ValueError):
+                encode([t], g)
+            return
+        rec = encode([t], g)
+        validate(rec, g)
+        assert rec[0, 0] == 2 * rn.count_leaves(t) - 1
+        assert decode_to_tuple(rec[0], g) == t
+        name = decode_to_name(rec[0], g)
+        assert rn.parse_name(name) == t and np.array_equal(encode([name], g), rec)
+
+    run()
+
+
 def test_encode_rejects_bad_input():
     g = Grammar.get("CKSHighDimSearchSpace", 2)
     with pytest.raises(ValueError):
