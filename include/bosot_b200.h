@@ -23,6 +23,14 @@
  *                               EI / GP-UCB formulas of BayesianOptimizerObjects.acquisition_function
  *                               (bayesian_optimization/bayesian_optimizer_objects.py:159-168)
  *   bosot_max_f64 ............. current_max = np.max(pred_mu_data) (same file, :165)
+ *   bosot_acquire_host / _device  the whole acquisition_function call (same file, :159-168) on flat trees
+ *   bosot_*_scatter ........... the same for a pool that is row-sharded over the GPUs of one node (no reference
+ *                               counterpart: the reference is single-process)
+ *   bosot_gp_nll_grad ......... GPR.training_loss + gradient for the ML-II fit (models/gp_model.py:162-199)
+ *   bosot_neighbours, bosot_host_choices, bosot_host_recursive_dataset
+ *                               the candidate producers (kernels/kernel_grammar/kernel_grammar_search_spaces.py:97-151,
+ *                               kernel_grammar_candidate_generator.py:85-111)
+ *   bosot_hellinger_* ......... the alternative kernel-kernel (kernels/kernel_kernel_hellinger.py:104-259)
  *
  * All device pointers must belong to the current CUDA device of the calling thread.
  * Every call is asynchronous on the given stream (a cudaStream_t passed as void*),
