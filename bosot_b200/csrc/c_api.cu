@@ -67,7 +67,7 @@ static WorkLayout work_layout(int64_t n_cand, int n_eval) {
   W.off_sigma = o;  o = align16(o + sizeof(double) * (size_t)n_cand);
   W.off_acq = o;    o = align16(o + sizeof(double) * (size_t)n_cand);
   W.off_status = o; o = align16(o + sizeof(int32_t) * (size_t)n_cand);
-  W.off_recs = o;   o = align16(o + pairs_scratch_bytes(n_cand));
+  W.off_recs = o;   o = align16(o + pairs_scratch_bytes(n_cand) + 16 * 16);  // + one 16-byte scratch head per chunk of the pipelined path
   W.total = o;
   return W;
 }
@@ -107,6 +107,7 @@ extern "C" size_t bosot_acquire_work_bytes(int64_t n_cand, int n_eval) {
 // helper streams / events for the pipelined host entry point (created lazily, one set per device, never destroyed)
 namespace bosot {
 constexpr int kMaxChunks = 16;
+static_assert(kMaxChunks == 16, "work_layout() reserves one 16-byte scratch head per chunk: 16 * 16 bytes");
 struct HostPipe {
   bool ready = false;
   cudaStream_t h2d = nullptr, d2h = nullptr, alt = nullptr;  // alt: second compute stream (odd chunks)
@@ -260,8 +261,8 @@ extern "C" int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const 
     cudaStream_t cs = (k & 1) ? P->alt : st;
     if (int rc = cuda_check(cudaStreamWaitEvent(cs, P->copied[k], 0), "cudaStreamWaitEvent")) return rc;
     if (int rc = launch_pairs(d_trees + c0 * kTreeBytes, n, grammar, d_eval_blob, n_eval, weights, variance, lengthscale,
-                              d_K + c0 * W.ld, nullptr, nullptr, W.ld, d_status + c0, d_recs + (size_t)c0 * kScanBytes,
-                              pairs_scratch_bytes(n), cs)) return rc;
+                              d_K + c0 * W.ld, nullptr, nullptr, W.ld, d_status + c0, d_recs + (size_t)c0 * kScanBytes + 16 * (size_t)k,
+                              pairs_scratch_bytes(n), cs)) return rc;  // chunk k: its own scratch head, then its records
     if (int rc = launch_posterior(d_K + c0 * W.ld, n, W.ld, n_eval, d_Linv, ldl, d_beta, mean_c, variance, acq_kind, d_current_max,
                                   xi, ucb_beta, h_mu ? d_mu + c0 : nullptr, h_sigma ? d_sigma + c0 : nullptr,
                                   h_acq ? d_acq + c0 : nullptr, cs)) return rc;

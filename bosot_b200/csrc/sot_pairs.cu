@@ -30,7 +30,6 @@
 //                                      The next tree's record is prefetched into registers while the
 //                                      current one is processed.
 #include <atomic>
-#include <mutex>
 #include "sot_common.cuh"
 #include "launch.cuh"
 #include "fast_math.cuh"
@@ -576,28 +575,9 @@ static int ensure_recip_table() {
   return BOSOT_OK;
 }
 
-// Work counters of the pair launches: a small per-device ring in global memory (allocated once, never freed); every
-// bosot_sot_pairs call takes the next one, its scan launch zeroes it.  64 calls may be in flight per device.
-constexpr int kCounterRing = 64;
-static unsigned long long* g_counters[64] = {nullptr};
-static std::atomic<unsigned> g_counter_seq[64];
-static std::mutex g_counter_mutex;
-
-static int next_counter(int dev, unsigned long long** out) {
-  if (dev < 0 || dev >= 64) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: device index out of range");
-  if (!g_counters[dev]) {
-    std::lock_guard<std::mutex> lock(g_counter_mutex);
-    if (!g_counters[dev]) {
-      void* ptr = nullptr;
-      if (int rc = cuda_check(cudaMalloc(&ptr, sizeof(unsigned long long) * kCounterRing), "cudaMalloc(work counters)")) return rc;
-      g_counters[dev] = static_cast<unsigned long long*>(ptr);
-    }
-  }
-  *out = g_counters[dev] + (g_counter_seq[dev].fetch_add(1u) % kCounterRing);
-  return BOSOT_OK;
-}
-
-size_t pairs_scratch_bytes(int64_t n_cand) { return align16((size_t)n_cand * kScanBytes); }
+// scratch of one call = 16 bytes (the work counter of the pair launch) + the compact records
+constexpr size_t kScratchHead = 16;
+size_t pairs_scratch_bytes(int64_t n_cand) { return align16(kScratchHead + (size_t)n_cand * kScanBytes); }
 
 int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar, const void* d_eval_blob,
                  int n_eval, const double weights[3], double variance, double lengthscale, double* d_K, double* d_D,
@@ -626,7 +606,8 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   p.D = d_D;
   p.Df = d_Df;
   p.ld = ld;
-  p.recs = static_cast<const uint8_t*>(d_scratch);
+  p.next = static_cast<unsigned long long*>(d_scratch);
+  p.recs = static_cast<const uint8_t*>(d_scratch) + kScratchHead;
 
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -641,9 +622,8 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   }
   const int64_t scan_blocks = (n_cand + kScanThreads - 1) / kScanThreads;
   if (scan_blocks > 0x7fffffffLL) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: too many candidates");
-  if (int rc = next_counter(dev, &p.next)) return rc;
   scan_kernel<<<(unsigned)scan_blocks, kScanThreads, kScanThreads * kRecBytes, stream>>>(
-      d_trees, n_cand, grammar->n_symbols, static_cast<uint8_t*>(d_scratch), d_status, p.next);
+      d_trees, n_cand, grammar->n_symbols, static_cast<uint8_t*>(d_scratch) + kScratchHead, d_status, p.next);
   if (int rc = after_launch("scan_kernel")) return rc;
 
   // launch 2: pairs.  One persistent CTA per SM; small pools shrink the CTA so that every SM gets warps.

@@ -147,7 +147,7 @@ int bosot_eval_info(const void* d_blob, int n_eval, int32_t h_info[4], void* str
  * Outputs are [n_cand][ld] fp64 with leading dimension ld >= n_eval (Df: 3 planes of
  * n_cand*ld); any of d_K / d_D / d_Df may be NULL.  d_status: int32[n_cand] tree defects (may be NULL).
  * d_scratch: device scratch of bosot_sot_pairs_scratch_bytes(n_cand) bytes, 16-byte aligned
- * (compact per-tree records between the scan launch and the pair launch).
+ * (the work counter of the pair launch, then the compact per-tree records that the scan launch hands to it).
  */
 size_t bosot_sot_pairs_scratch_bytes(int64_t n_cand);
 int bosot_sot_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,
