@@ -25,6 +25,7 @@ OP_MUL = 0x81
 PAD = 0xFF
 ACQ_NONE, ACQ_EI, ACQ_UCB = 0, 1, 2
 ERAW = -4  # bosot_host_*: block of raw generator outputs too short
+ABI_VERSION = 2
 
 
 class BosotGrammar(C.Structure):
@@ -68,6 +69,7 @@ _G = C.POINTER(BosotGrammar)
 SIGNATURES = {
     "bosot_last_error": (C.c_char_p, []),
     "bosot_abi_version": (C.c_int, []),
+    "bosot_shutdown": (C.c_int, []),
     "bosot_featurize": (C.c_int, [_P, C.c_int64, _G] + [_P] * 11 + [_P]),
     "bosot_eval_state_bytes": (C.c_size_t, [C.c_int]),
     "bosot_eval_build": (C.c_int, [_P, C.c_int, _G, _P, C.c_size_t, _P, _P]),
@@ -84,12 +86,17 @@ SIGNATURES = {
     "bosot_acquire_host": (
         C.c_int,
         [_P, C.c_int64, _G, _P, C.c_int, _D3, C.c_double, C.c_double, _P, C.c_int, _P, C.c_double, C.c_int, _P, C.c_double, C.c_double,
-         _P, C.c_size_t, _P, _P, _P, _P],
+         _P, C.c_size_t, _P, _P, _P, _P, _P],
     ),
     "bosot_acquire_device": (
         C.c_int,
         [_P, C.c_int64, _G, _P, C.c_int, _D3, C.c_double, C.c_double, _P, C.c_int, _P, C.c_double, C.c_int, _P, C.c_double, C.c_double,
-         _P, C.c_size_t, _P, _P, _P, _P],
+         _P, C.c_size_t, _P, _P, _P, _P, _P],
+    ),
+    "bosot_acquire_host_scatter": (
+        C.c_int,
+        [_P, C.c_int64, _G, _P, C.c_int, _D3, C.c_double, C.c_double, _P, C.c_int, _P, C.c_double, C.c_int, _P, C.c_double, C.c_double,
+         _P, C.c_size_t, _P, _P, _P, _P, _P, C.c_int, C.c_int64, _P],
     ),
     "bosot_posterior_acq_scatter": (
         C.c_int,
@@ -99,7 +106,7 @@ SIGNATURES = {
     "bosot_acquire_device_scatter": (
         C.c_int,
         [_P, C.c_int64, _G, _P, C.c_int, _D3, C.c_double, C.c_double, _P, C.c_int, _P, C.c_double, C.c_int, _P, C.c_double, C.c_double,
-         _P, C.c_size_t, _P, _P, _P, _P, C.c_int, C.c_int64, _P],
+         _P, C.c_size_t, _P, _P, _P, _P, _P, C.c_int, C.c_int64, _P],
     ),
     "bosot_neighbours": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P, _P]),
     "bosot_host_choices": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
@@ -137,7 +144,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = header / library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.bosot_abi_version() != 1:
+    if lib.bosot_abi_version() != ABI_VERSION:
         raise BosotLibraryError("bosot_b200: ABI version mismatch")
     _lib = lib
     return lib

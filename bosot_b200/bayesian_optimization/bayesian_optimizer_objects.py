@@ -8,6 +8,7 @@ evaluated-set state (index, Gram, Cholesky, current_max) prepared once per model
 being recomputed inside every call.
 """
 import logging
+import random
 import time
 from typing import List
 
@@ -93,7 +94,7 @@ class BayesianOptimizerObjects:
     # ---- one BO step --------------------------------------------------------------------------
     def update(self, step: int):
         if self.acquisition_function_type == AcquisitionFunctionType.RANDOM:
-            return np.random.choice(self.candidates), None
+            return random.choice(self.candidates), None  # Python's generator, like the reference (BOO:136-137)
         if self.acquisition_function_type == AcquisitionFunctionType.EXPECTED_IMPROVEMENT_PER_SECOND:
             self.duration_time_predictor.fit(self.x_data, self.query_durations_x_data)
         self.model.reset_model()
@@ -142,6 +143,7 @@ class BayesianOptimizerObjects:
             flat = self.model.kernel.flatten(self.model.transform_input(x_grid))
             _, _, acq = engine.acquire_device(flat.trees)
             acquisition_function = acq.cpu().numpy()
+            engine.raise_on_bad_trees()  # the stream is idle after the copy: reading the count costs one 4-byte D2H
         else:
             # PREDICT_Y: sigma carries the observation noise; same host formulas as the reference
             pred_mu_grid, pred_sigma_grid = self.model.predictive_dist(x_grid)

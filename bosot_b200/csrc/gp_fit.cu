@@ -201,7 +201,7 @@ extern "C" int bosot_gp_nll_grad(const double* d_Df, int n_eval, int64_t ld, con
   const size_t smem = sizeof(double) * ((size_t)n_eval * (n_eval | 1) + 3 * (size_t)n_eval + 32);
   static std::atomic<bool> attr_set[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
   int dev = 0;
-  cudaGetDevice(&dev);
+  if (int rc = cuda_check(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
   if (!(dev < 64 && attr_set[dev])) {
     if (int rc = cuda_check(cudaFuncSetAttribute(gp_nll_grad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024),
                             "cudaFuncSetAttribute(gp_nll_grad_kernel<16>)")) return rc;

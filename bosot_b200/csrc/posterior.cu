@@ -229,7 +229,7 @@ __host__ __device__ inline WsLayout ws_layout(int E) {
   WsLayout W;
   W.tld = post_tile_ld(E);
   W.n_blk = (E + kRowBlk - 1) / kRowBlk;
-  size_t o = 64;  // full[2], next_work, done[2], epi[2]
+  size_t o = 64;  // full[2], next_work, done[2], epi[2], issued[2]
   W.off_ks = o;   o += sizeof(double) * 2 * (size_t)TC * W.tld;
   W.off_red = o;  o += sizeof(double) * 2 * (size_t)W.n_blk * TC;
   W.off_mus = o;  o += sizeof(double) * 2 * TC;
@@ -250,6 +250,12 @@ posterior_ws_kernel(PostParams p) {
   int* next_work = reinterpret_cast<int*>(smem + 32);
   int* done = next_work + 1;  // [2]
   volatile int* epi = done + 2;  // [2] set while the epilogue of the tile that used the stage before still reads its sums / means
+  // issued[s] = 1 + number of the CTA tile whose copies were last issued into stage s.  full[s] alternates its phase
+  // parity per use, and try_wait.parity on the parity of the phase BEFORE the current one returns true at once, so a
+  // unit of tile i + 2 that reaches the barrier while tile i has not even landed (few units per tile: E <= 96, eight
+  // warps claim units of four consecutive tiles) would sail through.  A unit therefore first waits until ITS tile
+  // has been issued -- at that point every earlier phase of the barrier is complete and the parity wait is exact.
+  volatile int* issued = epi + 2;  // [2]
   double* Ks = reinterpret_cast<double*>(smem + W.off_ks);
   double* red = reinterpret_cast<double*>(smem + W.off_red);
   double* mus = reinterpret_cast<double*>(smem + W.off_mus);
@@ -262,7 +268,7 @@ posterior_ws_kernel(PostParams p) {
   if (threadIdx.x == 0) {
     ws_mbar_init(&full[0], 1); ws_mbar_init(&full[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    *next_work = 0; done[0] = 0; done[1] = 0; epi[0] = 0; epi[1] = 0;
+    *next_work = 0; done[0] = 0; done[1] = 0; epi[0] = 0; epi[1] = 0; issued[0] = 0; issued[1] = 0;
   }
   for (int x = threadIdx.x; x < (int)((W.total - W.off_ks) / sizeof(double)); x += kWsThreads) Ks[x] = 0.0;  // everything finite
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");             // generic-proxy zeros before async-proxy writes
@@ -278,6 +284,8 @@ posterior_ws_kernel(PostParams p) {
     __syncwarp();
     double* dst = Ks + (size_t)s * TC * tld;
     for (int c = lane; c < rows; c += 32) ws_tma_g2s(dst + (size_t)c * tld, p.Kstar + (c0 + c) * p.ld, row_bytes, &full[s]);
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); issued[s] = i + 1; }  // after expect_tx: the barrier is in tile i's phase now
   };
   if (warp == 0) {
     if (n_my > 0) issue_tile(0);
@@ -292,6 +300,7 @@ posterior_ws_kernel(PostParams p) {
     const int i = w / n_units, u = w - i * n_units;
     if (i >= n_my) break;
     const int s = i & 1;
+    while (issued[s] < i + 1) {}  // see issued[] above
     ws_mbar_wait(&full[s], (i >> 1) & 1);
     const double* Kt = Ks + (size_t)s * TC * tld;
     double* red_s = red + (size_t)s * n_blk * TC;
@@ -308,7 +317,8 @@ posterior_ws_kernel(PostParams p) {
       for (int nb = 0; nb < NB; ++nb) { up[nb][0] = up[nb][1] = 0.0; lo[nb][0] = lo[nb][1] = 0.0; }
       // Software pipeline: A fragments (L^-1, from L2) run kPD k-steps ahead in a register ring, B fragments
       // (K* tile, shared memory) one k-step ahead, so the 16 DMMAs of a step never wait on a load of that step.
-      // The k range is padded to a multiple of kPD: the extra steps multiply structural zeros of L^-1.
+      // The k range is padded to a multiple of kPD; the extra steps only load (their B columns may belong to the next
+      // candidate's row, which can hold NaN when that record was malformed), they issue no DMMA.
       constexpr int kPD = 4;
       const int KS = p.ldl >> 2;
       const double* a_up = p.Linv + (size_t)(2 * m) * KS * 32 + lane;  // one coalesced 256-byte fragment per k-step
@@ -339,7 +349,7 @@ posterior_ws_kernel(PostParams p) {
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) dmma8x8x4(up[nb][0], up[nb][1], au, bf[u & 1][nb]);
           }
-          if (lower_live) {
+          if (lower_live && ks < nks) {  // the padding steps of the pipeline read past the row: never multiply them
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) dmma8x8x4(lo[nb][0], lo[nb][1], al, bf[u & 1][nb]);
           }
@@ -587,7 +597,7 @@ int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_ev
   p.peers = d_peers; p.n_peers = d_peers ? n_peers : 0; p.peer_off = peer_off;
 
   int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
+  if (int rc = cuda_check(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
   if (int rc = cuda_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return rc;
   const size_t smem_cap = 226 * 1024;
 

@@ -40,7 +40,21 @@ constexpr int kMaxPairWarps = 28;   // one persistent CTA of up to 28 warps per 
 constexpr int kScanThreads = 128;
 constexpr int kMaxR = 8;            // evaluated trees per lane per register tile (E <= 256 in one pass, else tiles of 256)
 
-__constant__ double c_recip[64];  // 1/T for T = 1..63 ([0] unused)
+// Small tables, initialised STATICALLY (constant-folded by the host compiler, so correctly rounded like Python's
+// float(a) / float(b)): nothing is uploaded at run time, hence nothing to order against the caller's stream.
+struct RecipTable {  // v[T] = 1 / T for T = 1..63 ([0] unused)
+  double v[64];
+  constexpr RecipTable() : v{} { for (int t = 1; t < 64; ++t) v[t] = 1.0 / (double)t; }
+};
+struct FracTable {   // v[c * 33 + t] = (double)c / (double)t (optimal_transport_mappings.py:104-106), t = 0 -> 0
+  double v[33 * 33];
+  constexpr FracTable() : v{} {
+    for (int c = 0; c < 33; ++c)
+      for (int t = 1; t < 33; ++t) v[c * 33 + t] = (double)c / (double)t;
+  }
+};
+__constant__ RecipTable c_recip = RecipTable();
+__device__ const FracTable g_frac = FracTable();
 
 struct PairParams {
   const uint8_t* trees;
@@ -55,6 +69,7 @@ struct PairParams {
   int64_t ld;
   const uint8_t* recs;  // compact records written by scan_kernel: [n_cand][kScanBytes]
   unsigned long long* next;  // work counter (zeroed by the scan launch): the warps claim candidates one at a time
+  int32_t* bad;              // optional: number of malformed candidate records met (their rows are poisoned)
 };
 
 // per-warp shared memory: candidate dim-wise vector, block-state distance table, walk segments, accumulators, symbol counts
@@ -130,9 +145,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---- launch 1: thread-per-tree scan -> compact records ------------------------------------
 __global__ void __launch_bounds__(kScanThreads)
 scan_kernel(const uint8_t* __restrict__ trees, int64_t n_trees, int n_symbols, uint8_t* __restrict__ recs_out,
-            int32_t* __restrict__ status, unsigned long long* __restrict__ next) {
+            int32_t* __restrict__ status, unsigned long long* __restrict__ next, int32_t* __restrict__ bad_zero) {
   extern __shared__ __align__(16) uint8_t smem[];
-  if (blockIdx.x == 0 && threadIdx.x == 0) *next = 0ULL;  // work counter of the pair launch that follows on the stream
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *next = 0ULL;  // work counter of the pair launch that follows on the stream
+    if (bad_zero) *bad_zero = 0;  // ... and its count of malformed records
+  }
   const int64_t base = (int64_t)blockIdx.x * kScanThreads;
   const int in_block = (int)min((int64_t)kScanThreads, n_trees - base);
   for (int w = threadIdx.x; w < in_block * 4; w += kScanThreads) {  // coalesced: 16 B per thread
@@ -223,8 +241,6 @@ __device__ __forceinline__ void exp_nonpos_group(double (&x)[G]) {
 __device__ __forceinline__ double u32_to_f64(uint32_t m) {
   return __hiloint2double(0x43300000, (int)m) - 4503599627370496.0;
 }
-
-__device__ double g_frac[33 * 33];  // g_frac[c * 33 + t] = (double)c / (double)t (correctly rounded, filled by the host)
 
 template <int R, bool kExtra>  // R: evaluated trees per lane per tile; kExtra: also write D and/or Df
 __global__ void __launch_bounds__(kMaxPairWarps * 32, 1)
@@ -332,11 +348,15 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     if (bad) {  // malformed record: poison the row, status already written by the scan (cold path: keep it small)
       const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 #pragma unroll 1
-      for (int e = lane; e < E; e += 32) {
-        if (p.K) p.K[row + e] = qnan;
-        if (p.D) p.D[row + e] = qnan;
-        if (p.Df) { p.Df[row + e] = qnan; p.Df[plane + row + e] = qnan; p.Df[2 * plane + row + e] = qnan; }
+      for (int e = lane; e < ld_i; e += 32) {  // padding columns stay finite like those of every other row
+        const double v = e < E ? qnan : 0.0;
+        if (p.K) p.K[row + e] = v;
+        if (e < E) {
+          if (p.D) p.D[row + e] = v;
+          if (p.Df) { p.Df[row + e] = v; p.Df[plane + row + e] = v; p.Df[2 * plane + row + e] = v; }
+        }
       }
+      if (lane == 0 && p.bad) atomicAdd(p.bad, 1);
       continue;
     }
 
@@ -385,7 +405,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
       const int b = g.sym_block[s], j = meta->sym_pos[s];
       if (b >= 0 && j >= 0) {
         const uint32_t tot = btot[b];
-        avec[j] = tot ? __ldg(&g_frac[scnt[s] * 33u + tot]) : 0.0;
+        avec[j] = tot ? __ldg(&g_frac.v[scnt[s] * 33u + tot]) : 0.0;
       }
     }
     if (lane < g.n_blocks) avec[meta->null_pos[lane]] = btot[lane] == 0u ? 1.0 : 0.0;
@@ -447,7 +467,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     __syncwarp();
 
     // ---- phase C: register tiles of R evaluated trees per lane (tree e = e0 + lane + 32 r)
-    const double rTa2_sub = 2.0 * c_recip[nn], rTa2_path = 2.0 * c_recip[nl];
+    const double rTa2_sub = 2.0 * c_recip.v[nn], rTa2_path = 2.0 * c_recip.v[nl];
     for (int e0 = 0; e0 < E; e0 += 32 * R) {
       const int eb = e0 + lane;  // e_pad is a whole number of tiles: eb + 32 r < e_pad, padded arrays stay in bounds
       uint32_t msub2[RP];
@@ -557,31 +577,14 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   }
 }
 
-static std::atomic<bool> g_recip_ready[64];  // per device, zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
-
-static int ensure_recip_table() {
-  int dev = 0;
-  if (int rc = cuda_check(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
-  if (dev < 64 && g_recip_ready[dev]) return BOSOT_OK;
-  double h[64];
-  h[0] = 0.0;
-  for (int t = 1; t < 64; ++t) h[t] = 1.0 / (double)t;
-  if (int rc = cuda_check(cudaMemcpyToSymbol(c_recip, h, sizeof(h)), "cudaMemcpyToSymbol(c_recip)")) return rc;
-  double frac[33 * 33];  // count / total like the reference's float(a) / float(b) (optimal_transport_mappings.py:104-106)
-  for (int c = 0; c < 33; ++c)
-    for (int t = 0; t < 33; ++t) frac[c * 33 + t] = t ? (double)c / (double)t : 0.0;
-  if (int rc = cuda_check(cudaMemcpyToSymbol(g_frac, frac, sizeof(frac)), "cudaMemcpyToSymbol(g_frac)")) return rc;
-  if (dev < 64) g_recip_ready[dev] = true;
-  return BOSOT_OK;
-}
-
 // scratch of one call = 16 bytes (the work counter of the pair launch) + the compact records
 constexpr size_t kScratchHead = 16;
 size_t pairs_scratch_bytes(int64_t n_cand) { return align16(kScratchHead + (size_t)n_cand * kScanBytes); }
 
 int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar, const void* d_eval_blob,
                  int n_eval, const double weights[3], double variance, double lengthscale, double* d_K, double* d_D,
-                 double* d_Df, int64_t ld, int32_t* d_status, void* d_scratch, size_t scratch_bytes, cudaStream_t stream) {
+                 double* d_Df, int64_t ld, int32_t* d_status, void* d_scratch, size_t scratch_bytes, cudaStream_t stream,
+                 int32_t* d_bad, bool zero_bad) {
   if (!grammar || !d_eval_blob || !weights || n_cand < 0 || (n_cand > 0 && (!d_trees || !d_scratch)))
     return set_error(BOSOT_EINVAL, "bosot_sot_pairs: null argument");
   if (n_eval < 1 || n_eval > BOSOT_MAX_EVAL) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: n_eval out of range");
@@ -590,7 +593,6 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
     return set_error(BOSOT_EINVAL, "bosot_sot_pairs: scratch too small or not 16-byte aligned (bosot_sot_pairs_scratch_bytes)");
   if (int rc = check_grammar(grammar)) return rc;
   if (n_cand == 0) return BOSOT_OK;
-  if (int rc = ensure_recip_table()) return rc;
 
   PairParams p;
   p.trees = d_trees;
@@ -607,10 +609,11 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   p.Df = d_Df;
   p.ld = ld;
   p.next = static_cast<unsigned long long*>(d_scratch);
+  p.bad = d_bad;
   p.recs = static_cast<const uint8_t*>(d_scratch) + kScratchHead;
 
   int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
+  if (int rc = cuda_check(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
   if (int rc = cuda_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return rc;
 
   // launch 1: scan
@@ -623,7 +626,7 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   const int64_t scan_blocks = (n_cand + kScanThreads - 1) / kScanThreads;
   if (scan_blocks > 0x7fffffffLL) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: too many candidates");
   scan_kernel<<<(unsigned)scan_blocks, kScanThreads, kScanThreads * kRecBytes, stream>>>(
-      d_trees, n_cand, grammar->n_symbols, static_cast<uint8_t*>(d_scratch) + kScratchHead, d_status, p.next);
+      d_trees, n_cand, grammar->n_symbols, static_cast<uint8_t*>(d_scratch) + kScratchHead, d_status, p.next, zero_bad ? d_bad : nullptr);
   if (int rc = after_launch("scan_kernel")) return rc;
 
   // launch 2: pairs.  One persistent CTA per SM; small pools shrink the CTA so that every SM gets warps.
@@ -679,5 +682,5 @@ extern "C" int bosot_sot_pairs(const uint8_t* d_trees, int64_t n_cand, const bos
                                double* d_K, double* d_D, double* d_Df, int64_t ld,
                                int32_t* d_status, void* d_scratch, size_t scratch_bytes, void* stream) {
   return bosot::launch_pairs(d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale, d_K, d_D,
-                             d_Df, ld, d_status, d_scratch, scratch_bytes, (cudaStream_t)stream);
+                             d_Df, ld, d_status, d_scratch, scratch_bytes, (cudaStream_t)stream, nullptr, false);
 }

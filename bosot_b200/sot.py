@@ -289,6 +289,9 @@ class AcquisitionEngine:
         self.current_max = max_f64(self.mu_data)
         self._work = None
         self._wdbl = _DBL3(*self.weights)
+        # malformed candidate records of the last acquire_* call (their rows are NaN): device count + pinned host copy
+        self._bad = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._h_bad = torch.zeros(1, dtype=torch.int32).pin_memory()
 
     def _workspace(self, n: int) -> torch.Tensor:
         need = _lib.load().bosot_acquire_work_bytes(n, self.n_eval)
@@ -302,7 +305,10 @@ class AcquisitionEngine:
 
         ``scatter = (peer_ptrs_dev, n_peers, row_offset)``: the posterior kernel additionally stores every acquisition
         value into the peer-mapped result vectors of all GPUs of the node at ``row_offset + i`` (C-ABI
-        ``bosot_acquire_device_scatter``; see ``bosot_b200.distributed.PeerScatter``)."""
+        ``bosot_acquire_device_scatter``; see ``bosot_b200.distributed.PeerScatter``).
+
+        The call does not synchronise; malformed records poison their own row with NaN and are counted on the device:
+        ``bad_tree_count()`` (synchronises) or ``raise_on_bad_trees()`` after the results have been read."""
         _need_cuda(trees, "candidate trees")
         n = trees.shape[0]
         if out is None:
@@ -313,7 +319,7 @@ class AcquisitionEngine:
         head = (trees.data_ptr(), n, C.byref(self.grammar.c_struct), self.state.blob.data_ptr(), self.n_eval, self._wdbl,
                 self.variance, self.lengthscale, self.Linv.data_ptr(), self.Linv.shape[1], self.beta.data_ptr(), self.mean_c,
                 self.acq_kind, self.current_max.data_ptr(), self.xi, self.ucb_beta, w.data_ptr(), w.numel(),
-                mu.data_ptr(), sigma.data_ptr(), acq.data_ptr())
+                mu.data_ptr(), sigma.data_ptr(), acq.data_ptr(), self._bad.data_ptr())
         with torch.cuda.device(self.device):
             if scatter is None:
                 rc = lib.bosot_acquire_device(*head, _stream(self.device))
@@ -323,22 +329,42 @@ class AcquisitionEngine:
         _lib.check(rc, "acquire_device")
         return mu, sigma, acq
 
-    def acquire_host(self, h_trees: torch.Tensor, h_acq: torch.Tensor, h_mu: Optional[torch.Tensor] = None,
-                     h_sigma: Optional[torch.Tensor] = None, sync: bool = True):
+    def bad_tree_count(self) -> int:
+        """Malformed candidate records met by the last ``acquire_device`` call (synchronises the stream)."""
+        return int(self._bad.item())
+
+    def raise_on_bad_trees(self) -> None:
+        n = self.bad_tree_count()
+        if n:
+            raise ValueError("bosot_b200: %d malformed flat tree record(s) among the candidates (their values are NaN)" % n)
+
+    def acquire_host(self, h_trees: torch.Tensor, h_acq: Optional[torch.Tensor], h_mu: Optional[torch.Tensor] = None,
+                     h_sigma: Optional[torch.Tensor] = None, sync: bool = True, scatter: Optional[Tuple[int, int, int]] = None):
         """End-to-end call with HOST buffers (pinned for async copies): H2D of the flat trees,
-        both kernels, D2H of the acquisition values (and mu / sigma when given)."""
-        if h_trees.is_cuda or h_acq.is_cuda:
+        both kernels, D2H of the acquisition values (and mu / sigma when given).  With ``scatter`` (see
+        ``acquire_device``) the rows are one rank's shard of a pool: the values additionally go to every GPU's
+        result vector (C-ABI ``bosot_acquire_host_scatter``) and ``h_acq`` may be None.
+        ``sync=True`` waits for the results and raises ``ValueError`` if a candidate record was malformed."""
+        if h_trees.is_cuda or (h_acq is not None and h_acq.is_cuda):
             raise ValueError("acquire_host takes host tensors")
+        if h_acq is None and scatter is None:
+            raise ValueError("acquire_host needs h_acq (or a scatter target)")
         n = h_trees.shape[0]
         w = self._workspace(n)
-        with torch.cuda.device(self.device):
-            rc = _lib.load().bosot_acquire_host(
-                h_trees.data_ptr(), n, C.byref(self.grammar.c_struct), self.state.blob.data_ptr(), self.n_eval, self._wdbl,
+        head = (h_trees.data_ptr(), n, C.byref(self.grammar.c_struct), self.state.blob.data_ptr(), self.n_eval, self._wdbl,
                 self.variance, self.lengthscale, self.Linv.data_ptr(), self.Linv.shape[1], self.beta.data_ptr(), self.mean_c,
                 self.acq_kind, self.current_max.data_ptr(), self.xi, self.ucb_beta, w.data_ptr(), w.numel(),
-                _ptr(h_mu), _ptr(h_sigma), h_acq.data_ptr(), _stream(self.device),
-            )
+                _ptr(h_mu), _ptr(h_sigma), _ptr(h_acq), self._h_bad.data_ptr())
+        with torch.cuda.device(self.device):
+            if scatter is None:
+                rc = _lib.load().bosot_acquire_host(*head, _stream(self.device))
+            else:
+                ptrs, n_peers, offset = scatter
+                rc = _lib.load().bosot_acquire_host_scatter(*head, ptrs, int(n_peers), int(offset), _stream(self.device))
         _lib.check(rc, "acquire_host")
         if sync:
             torch.cuda.current_stream(self.device).synchronize()
+            if int(self._h_bad[0]):
+                raise ValueError("bosot_b200: %d malformed flat tree record(s) among the candidates (their values are NaN)"
+                                 % int(self._h_bad[0]))
         return h_acq

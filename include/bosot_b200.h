@@ -33,9 +33,15 @@
  *   bosot_hellinger_* ......... the alternative kernel-kernel (kernels/kernel_kernel_hellinger.py:104-259)
  *
  * All device pointers must belong to the current CUDA device of the calling thread.
- * Every call is asynchronous on the given stream (a cudaStream_t passed as void*),
- * keeps no state besides caller-owned buffers, and returns 0 on success or a negative
- * BOSOT_E* code; it never throws or exits.  One call in flight per stream.
+ * Every call is asynchronous on the given stream (a cudaStream_t passed as void*; blocking and
+ * non-blocking streams alike: nothing is uploaded behind the caller's back, all tables are static
+ * data of the library) and returns 0 on success or a negative BOSOT_E* code; it never throws or
+ * exits.  One call in flight per stream.
+ * State: none besides caller-owned buffers, with ONE exception -- bosot_acquire_host /
+ * bosot_acquire_host_scatter keep, per device, three helper streams and a few events for their
+ * chunked copy/compute pipeline (created on the first call with >= 400000 candidates on that
+ * device, guarded by a per-device mutex that is held only while work is ENQUEUED, released by
+ * bosot_shutdown()).
  * fp64 throughout ("f64" path); the reference computes in float64 as well
  * (kernel_kernel_grammar_tree.py:35).
  */
@@ -49,7 +55,7 @@
 extern "C" {
 #endif
 
-#define BOSOT_ABI_VERSION 1
+#define BOSOT_ABI_VERSION 2
 
 /* ---- flat tree encoding ("one tree = one 64-byte record") -------------------
  * byte 0      : n = number of nodes (odd, 1..63)   => at most 32 leaves
@@ -95,6 +101,9 @@ typedef struct bosot_grammar {
 
 const char* bosot_last_error(void); /* thread-local message of the last failing call */
 int bosot_abi_version(void);
+/* Synchronises and destroys the helper streams / events of the host-buffer pipeline on every device (see "State"
+ * above).  Optional; the library can be used again afterwards (the pipeline is rebuilt on demand). */
+int bosot_shutdown(void);
 
 /* ---- featurisation (ordered sparse histograms) ---------------------------------
  * Per tree i (all arrays row-major, caller-allocated on the device):
@@ -187,9 +196,14 @@ int bosot_max_f64(const double* d_x, int64_t n, double* d_out, void* stream);
 
 /* ---- host-buffer convenience (the end-to-end call) --------------------------------------
  * Candidates in (preferably pinned) host memory -> acquisition values in host memory.
- * Copies h_trees to d_trees_scratch, runs pairs + posterior, copies acq (and mu/sigma when
- * non-NULL) back, all on `stream`; the caller synchronises the stream.
+ * Copies h_trees into d_work, runs pairs + posterior, copies acq (and mu/sigma when non-NULL) back, ordered
+ * on `stream`; the caller synchronises the stream.  Pools of >= 400000 candidates flow through a chunked
+ * H2D | kernels | D2H pipeline on helper streams that is joined back into `stream` before the call returns
+ * (also when it returns an error); with pageable host memory the copies (and so the call) block.
  * d_work: device scratch of bosot_acquire_work_bytes(n_cand, n_eval) bytes.
+ * h_n_bad / d_n_bad (int32, may be NULL): number of malformed candidate records of this call.  Their rows are
+ * NaN in every output (K* row poisoned), all other rows are unaffected; a caller that cannot rule malformed
+ * records out must check the count (0 = every value is valid) once the stream has been synchronised.
  */
 size_t bosot_acquire_work_bytes(int64_t n_cand, int n_eval);
 int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const bosot_grammar* grammar,
@@ -198,7 +212,7 @@ int bosot_acquire_host(const uint8_t* h_trees, int64_t n_cand, const bosot_gramm
                        const double* d_LinvF, int ldl, const double* d_beta, double mean_c,
                        int acq_kind, const double* d_current_max, double xi, double ucb_beta,
                        void* d_work, size_t work_bytes,
-                       double* h_mu, double* h_sigma, double* h_acq, void* stream);
+                       double* h_mu, double* h_sigma, double* h_acq, int32_t* h_n_bad, void* stream);
 
 /* same, candidates already on the device, outputs on the device */
 int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,
@@ -207,7 +221,7 @@ int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, const bosot_gra
                          const double* d_LinvF, int ldl, const double* d_beta, double mean_c,
                          int acq_kind, const double* d_current_max, double xi, double ucb_beta,
                          void* d_work, size_t work_bytes,
-                         double* d_mu, double* d_sigma, double* d_acq, void* stream);
+                         double* d_mu, double* d_sigma, double* d_acq, int32_t* d_n_bad, void* stream);
 
 /* ---- row-sharded pools: posterior + acquisition fused with the exchange of the result ----
  * The reference has no multi-process path; here the candidate pool is split into row blocks over the GPUs of one
@@ -230,8 +244,19 @@ int bosot_acquire_device_scatter(const uint8_t* d_trees, int64_t n_cand, const b
                                  const double* d_LinvF, int ldl, const double* d_beta, double mean_c,
                                  int acq_kind, const double* d_current_max, double xi, double ucb_beta,
                                  void* d_work, size_t work_bytes,
-                                 double* d_mu, double* d_sigma, double* d_acq,
+                                 double* d_mu, double* d_sigma, double* d_acq, int32_t* d_n_bad,
                                  const void* d_peer_ptrs, int n_peers, int64_t peer_offset, void* stream);
+/* The same from HOST buffers: this rank's shard of the pool runs through the pipeline of bosot_acquire_host (H2D of the
+ * shard | kernels | D2H of the shard's values into h_mu / h_sigma / h_acq, any of which may be NULL) while the posterior
+ * epilogue of every chunk stores the acquisition values into all peers at peer_offset + row. */
+int bosot_acquire_host_scatter(const uint8_t* h_trees, int64_t n_cand, const bosot_grammar* grammar,
+                               const void* d_eval_blob, int n_eval, const double weights[3],
+                               double variance, double lengthscale,
+                               const double* d_LinvF, int ldl, const double* d_beta, double mean_c,
+                               int acq_kind, const double* d_current_max, double xi, double ucb_beta,
+                               void* d_work, size_t work_bytes,
+                               double* h_mu, double* h_sigma, double* h_acq, int32_t* h_n_bad,
+                               const void* d_peer_ptrs, int n_peers, int64_t peer_offset, void* stream);
 
 /* ---- hyper-parameter fit of the GP over kernels ----------------------------------
  * One launch = one evaluation of GPR's training loss (negative log marginal likelihood; reference

@@ -110,7 +110,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     loaded = _lib.load()
-    assert loaded.bosot_abi_version() == 1
+    assert loaded.bosot_abi_version() == _lib.ABI_VERSION == 2
     assert loaded.bosot_eval_state_bytes(0) == 0 and loaded.bosot_eval_state_bytes(50) > 0
     assert loaded.bosot_acquire_work_bytes(10, 50) >= 10 * (56 * 8 + 64)
 
