@@ -317,8 +317,7 @@ posterior_ws_kernel(PostParams p) {
       for (int nb = 0; nb < NB; ++nb) { up[nb][0] = up[nb][1] = 0.0; lo[nb][0] = lo[nb][1] = 0.0; }
       // Software pipeline: A fragments (L^-1, from L2) run kPD k-steps ahead in a register ring, B fragments
       // (K* tile, shared memory) one k-step ahead, so the 16 DMMAs of a step never wait on a load of that step.
-      // The k range is padded to a multiple of kPD; the extra steps only load (their B columns may belong to the next
-      // candidate's row, which can hold NaN when that record was malformed), they issue no DMMA.
+      // The k range is padded to a multiple of kPD; the extra steps only load, they issue no DMMA.
       constexpr int kPD = 4;
       const int KS = p.ldl >> 2;
       const double* a_up = p.Linv + (size_t)(2 * m) * KS * 32 + lane;  // one coalesced 256-byte fragment per k-step
@@ -333,7 +332,9 @@ posterior_ws_kernel(PostParams p) {
       }
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) bf[0][nb] = bp[(size_t)nb * 8 * tld];
-      for (int ks0 = 0; ks0 < nks_pad; ks0 += kPD) {
+      // whole groups of kPD steps below nks run unguarded; the last, partly padded group guards its DMMAs
+      const int n_full = nks & ~(kPD - 1);
+      for (int ks0 = 0; ks0 < n_full; ks0 += kPD) {
 #pragma unroll
         for (int u = 0; u < kPD; ++u) {
           const int ks = ks0 + u;
@@ -342,16 +343,33 @@ posterior_ws_kernel(PostParams p) {
             ra_up[u] = __ldg(a_up + 32 * (ks + kPD));
             ra_lo[u] = lower_live ? __ldg(a_lo + 32 * (ks + kPD)) : 0.0;
           }
-          // next step's B fragments (after the last step this reads a few finite doubles past the row: never used)
 #pragma unroll
           for (int nb = 0; nb < NB; ++nb) bf[(u + 1) & 1][nb] = bp[(size_t)nb * 8 * tld + 4 * (ks + 1)];
           if (ks < nks_up) {
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) dmma8x8x4(up[nb][0], up[nb][1], au, bf[u & 1][nb]);
           }
-          if (lower_live && ks < nks) {  // the padding steps of the pipeline read past the row: never multiply them
+          if (lower_live) {
 #pragma unroll
             for (int nb = 0; nb < NB; ++nb) dmma8x8x4(lo[nb][0], lo[nb][1], al, bf[u & 1][nb]);
+          }
+        }
+      }
+      if (n_full < nks_pad) {
+#pragma unroll
+        for (int u = 0; u < kPD; ++u) {
+          const int ks = n_full + u;
+          // the B fragments of the padding steps (ks >= nks) may lie past the row, in the next candidate's row, which
+          // holds NaN when that record was malformed: they are loaded (uniform pipeline) but never multiplied
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) bf[(u + 1) & 1][nb] = bp[(size_t)nb * 8 * tld + 4 * (ks + 1)];
+          if (ks < nks_up) {
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) dmma8x8x4(up[nb][0], up[nb][1], ra_up[u], bf[u & 1][nb]);
+          }
+          if (lower_live && ks < nks) {
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) dmma8x8x4(lo[nb][0], lo[nb][1], ra_lo[u], bf[u & 1][nb]);
           }
         }
       }

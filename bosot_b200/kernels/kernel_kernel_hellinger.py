@@ -184,3 +184,6 @@ class HellingerAcquisitionEngine:
                 dst.copy_(src)
             return out
         return mu, sigma, acq
+
+    def raise_on_bad_trees(self) -> None:
+        """Same hook as ``sot.AcquisitionEngine``: ``hellinger.cross`` checks the per-tree status itself."""

@@ -121,10 +121,9 @@ def test_marginal_likelihood_and_gradient():
     # value against the NumPy restatement of GPR.log_marginal_likelihood
     trees = [rn.parse_name(str(e)) for e in x]
     hyp = rn.Hyper(noise_variance=1e-4, mean_c=0.2)
-    K = rn.K(trees, None, hyp, "CKSHighDimSearchSpace", 3) + 1e-4 * np.eye(30)
-    L = np.linalg.cholesky(K)
-    a = np.linalg.solve(L, y - 0.2)
-    lml = -0.5 * float((a * a).sum()) - np.log(np.diag(L)).sum() - 15 * np.log(2 * np.pi)
+    K_EE = rn.K(trees, None, hyp, "CKSHighDimSearchSpace", 3)
+    lml = rn.log_marginal_likelihood(K_EE, y, hyp)  # Cholesky route, as GPflow computes it
+    np.testing.assert_allclose(lml, rn.log_marginal_likelihood_direct(K_EE, y, hyp), rtol=1e-10)  # solve + slogdet route
     np.testing.assert_allclose(model.estimate_model_evidence(), lml, rtol=1e-9)
     # analytic (autograd) gradient against central differences in unconstrained space
     layout, theta, _ = model._pack()
@@ -256,6 +255,106 @@ def test_bo_loop_makes_the_same_selections_as_the_cpu_path():
     bo.sample_train_set(16)
     metrics, queries, *_ = bo.maximize(5)
     assert bo.calls == 15 and bo.same_argmax >= 13 and len(queries) == 5
+
+
+class _FittedOracleAcquisitionBO(BayesianOptimizerObjects):
+    """The reference's loop with the ML-II fit ON (BOO:143-144): every step re-fits the hyper-parameters of the GP
+    over kernels, reads (alphas, lengthscale, variance, noise, c) back from the model and hands them to the CPU
+    oracle, whose acquisition values drive the object EA.  Only the fit is shared with the GPU loop (it consumes the
+    global np.random stream through the perturbation, gp_model.py:263-282, so both loops must run it)."""
+
+    def __init__(self, gen_name, d, **kw):
+        super().__init__(**kw)
+        self._g, self._d = gen_name, d
+        self.hyper_trace, self.lml_checks = [], 0
+
+    def update(self, step):
+        from bosot_b200.bayesian_optimization.evolutionary_optimizer_objects import EvolutionaryOptimizerObjects
+
+        self.model.reset_model()
+        self.model.infer(self.x_data, self.y_data)
+        k = self.model.kernel
+        self._h = rn.Hyper(alphas=np.array(k.alphas.numpy(), copy=True), lengthscale=float(k.lengthscale), variance=float(k.variance),
+                           noise_variance=float(self.model.likelihood_variance), mean_c=self.model.mean_function.value())
+        self.hyper_trace.append((tuple(self._h.alphas), self._h.lengthscale, self._h.variance, self._h.noise_variance, self._h.mean_c))
+        # the objective the fit minimised, at its optimum, against the oracle's log marginal likelihood (both routes)
+        trees = [rn.parse_name(str(x)) for x in self.x_data]
+        K_EE = rn.K(trees, None, self._h, self._g, self._d)
+        lml = rn.log_marginal_likelihood(K_EE, self.y_data, self._h)
+        np.testing.assert_allclose(lml, rn.log_marginal_likelihood_direct(K_EE, self.y_data, self._h), rtol=1e-9)
+        np.testing.assert_allclose(-self.model.training_loss(), lml, rtol=1e-9, atol=1e-9)
+        self.lml_checks += 1
+        opt = EvolutionaryOptimizerObjects(self.population_evolutionary, self.num_offspring_evolutionary, self.candidate_generator)
+        q, _ = opt.maximize(self.acquisition_function, self.n_steps_evolutionary)
+        return q, None
+
+    def acquisition_function(self, x_grid):
+        t = lambda xs: [rn.parse_name(str(x)) for x in xs]  # noqa: E731
+        kind = "UCB" if self.acquisition_function_type == AcquisitionFunctionType.GP_UCB else "EI"
+        return rn.acquisition_function(t(self.x_data), self.y_data, t(x_grid), self._h, self._g, self._d, kind=kind)["acq"]
+
+
+class _TracedBO(BayesianOptimizerObjects):
+    """GPU loop that records the hyper-parameters every model update ends with."""
+
+    def __init__(self, **kw):
+        super().__init__(**kw)
+        self.hyper_trace = []
+
+    def update(self, step):
+        out = super().update(step)
+        k = self.model.kernel
+        self.hyper_trace.append((tuple(np.array(k.alphas.numpy(), copy=True)), float(k.lengthscale), float(k.variance),
+                                 float(self.model.likelihood_variance), self.model.mean_function.value()))
+        return out
+
+
+def _fitted_toy_model(d):
+    """The toy example's model (bosot/examples/bayesian_optimization_kernel_space.py:87-95): ML-II fit with random
+    perturbation, no multi-start, PREDICT_F, trainable constant mean."""
+    model = ModelFactory.build(BasicObjectGPModelConfig(
+        kernel_config=OTWeightedDimsExtendedGrammarKernelConfig(input_dimension=d), optimize_hps=True,
+        perform_multi_start_optimization=False, prediction_quantity=PredictionQuantity.PREDICT_F))
+    model.set_mean_function(ObjectConstant())
+    return model
+
+
+@pytest.mark.parametrize("acq", ["UCB", "EI"])
+def test_bo_loop_with_hyperparameter_fit_makes_the_same_selections_as_the_cpu_path(acq):
+    """north_star: "identical BO kernel selections on the toy example" -- with the ML-II fit ON, as the reference
+    runs it (reset_model(); infer() every step, BOO:143-144, gp_model.py:162-193).  Three loops from the same seed:
+    GPU with the flat (device-resident) EA, GPU with the object EA, and the loop whose acquisition values come from
+    the CPU oracle evaluated at the hyper-parameters each fit ended with.  All three must query the same kernels in
+    the same order for 5 steps; the fits must end at the same hyper-parameters, and their objective must equal the
+    oracle's log marginal likelihood there."""
+    from bosot_b200.bayesian_optimization.enums import AcquisitionOptimizationObjectBOType
+
+    d, space = 2, "CKSWithRQSearchSpace"
+    cfg_cls = ObjectBOGPUCBConfig if acq == "UCB" else ObjectBOExpectedImprovementEAConfig
+    cfg = cfg_cls(n_steps_evolutionary=3, population_evolutionary=50, num_offspring_evolutionary=4).dict()
+    cfg["acquisiton_optimization_type"] = AcquisitionOptimizationObjectBOType.EVOLUTIONARY
+    runs = {}
+    for which in ("gpu_flat", "gpu_object", "cpu"):
+        gen = GeneratorFactory.build(CKSWithRQGeneratorConfig(input_dimension=d))
+        if which == "cpu":
+            bo = _FittedOracleAcquisitionBO(space, d, **cfg)
+        else:
+            bo = _TracedBO(**cfg)
+            bo.use_flat_evolutionary = which == "gpu_flat"
+        bo.set_model(_fitted_toy_model(d))
+        bo.set_oracle(StructuralOracle([str(r) for r in gen.search_space.get_root_expressions()], seed=3))
+        bo.set_candidate_generator(gen)
+        np.random.seed(42)
+        bo.sample_train_set(16)
+        _, queries, *_ = bo.maximize(5)
+        runs[which] = ([str(q) for q, _ in queries], bo.hyper_trace)
+        if which == "cpu":
+            assert bo.lml_checks == 5
+    assert runs["gpu_flat"][0] == runs["gpu_object"][0] == runs["cpu"][0], runs
+    for a, b in zip(runs["gpu_flat"][1], runs["cpu"][1]):  # same fit, same np.random stream: the same optimum
+        np.testing.assert_allclose(np.hstack([np.ravel(x) for x in a]), np.hstack([np.ravel(x) for x in b]), rtol=1e-9)
+    trained = np.array([np.hstack([np.ravel(x) for x in h]) for h in runs["cpu"][1]])
+    assert np.ptp(trained, axis=0).max() > 1e-3  # the fit really moved the hyper-parameters between steps
 
 
 def test_flat_and_object_evolutionary_modes_agree():

@@ -97,3 +97,23 @@ def test_invariants_commutativity_and_ranges():
     for f, s in ((rn.DIM_WISE, d), (rn.PATHS, 1), (rn.SUBTREES, 1)):
         F, _ = rn.dense_features(X, None, f, gen, d)
         np.testing.assert_allclose(F.sum(axis=1), s, rtol=1e-14)
+
+
+def test_independent_restatements_agree(golden):
+    """The arithmetic half cannot be pinned by executing TF / GPflow here, so the posterior (a9) and the marginal
+    likelihood of the fit (f1) are restated twice through routes that share no factorisation -- Cholesky + triangular
+    solves as GPflow's base_conditional does it, and a general solve / slogdet -- and must agree to 1e-10."""
+    gen, d = str(golden["generator_name"]), int(golden["input_dimension"])
+    xe, xc = _trees(golden, "eval_names"), _trees(golden, "cand_names")
+    y = golden["y"]
+    for h in (rn.Hyper(**rn.H0), rn.Hyper(**rn.H1), rn.Hyper(alphas=(0.9, 0.1, 0.6), lengthscale=2.5, variance=0.4, noise_variance=1e-2, mean_c=1.5)):
+        K_EE, K_EN = rn.K(xe, None, h, gen, d), rn.K(xe, xc, h, gen, d)
+        Knn = rn.K_diag(xc, h, gen, d, literal=False)
+        mu, sigma = rn.gp_posterior_from_grams(K_EE, K_EN, Knn, y, h)
+        mu2, var2 = rn.gp_posterior_direct(K_EE, K_EN, Knn, y, h)
+        np.testing.assert_allclose(mu, mu2, rtol=1e-10, atol=1e-10)
+        ok = np.isfinite(sigma)
+        np.testing.assert_allclose(sigma[ok] ** 2, var2[ok], rtol=1e-10, atol=1e-10)
+        assert np.all(var2[~ok] < 1e-10)  # sqrt of a rounding-negative variance: both routes see (numerically) zero
+        a, b = rn.log_marginal_likelihood(K_EE, y, h), rn.log_marginal_likelihood_direct(K_EE, y, h)
+        np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-10)
