@@ -125,8 +125,12 @@ def run_reference(args, rank: int) -> None:
                     sample="%d candidates x %d evaluated per step (bounded sample of the 1M pool)" % (sample, N_EVAL)),
         ei_candidates_per_sec=sample / sec,
         cpu_baseline=dict(value=value, unit="pairs/s", cores=cores, kind="port",
-                          sample="%d candidates x %d evaluated per step, %d worker processes x calls of 100 candidates; "
-                                 "K_diag taken as variance" % (sample, N_EVAL, cores)),
+                          sample="%d candidates x %d evaluated per step, %d worker processes (1 BLAS thread each) x calls of 100 "
+                                 "candidates; K_diag taken as variance" % (sample, N_EVAL, cores),
+                          pair_distances_computed_per_call=r["pair_distances_computed_per_call"],
+                          pair_distances_credited_per_call=r["pair_distances_credited_per_call"],
+                          note="a reference-shaped call recomputes the E x E Gram three times (predict_f at the evaluated "
+                               "kernels and at the candidates): only candidates x evaluated pairs are credited"),
         e2e=dict(value=value, unit="pairs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
         gpu_launches=0,
     )
@@ -227,18 +231,22 @@ def main() -> None:
         # N = 1: host flat trees -> device -> EI -> host through the host-buffer entry point
         eng.acquire_host(h_ca, h_ei, sync=True)
 
-    d_stage = torch.empty_like(d_ca)
+    h_ei_shard = h_ei[lo:hi] if world > 1 else h_ei  # this rank's rows of the result (pinned)
+    d_stage = torch.empty_like(d_ca) if (world > 1 and scatter is None) else None
 
     def step_e2e_multi():
-        # N > 1: pinned H2D of the shard, kernels, exchange of the EI shards on the device, pinned D2H of the full EI vector
-        d_stage.copy_(h_ca, non_blocking=True)
+        # N > 1: every rank runs the SAME host-buffer pipeline as N = 1 on its shard (C-ABI bosot_acquire_host_scatter:
+        # chunked H2D | kernels | D2H of the shard's EI values into this rank's pinned rows) while the posterior epilogue
+        # stores the values into every GPU's vector over NVLink; one barrier closes the step.  Afterwards the host holds
+        # the pool's EI values (each rank its rows) and every GPU holds the whole vector.
         if scatter is not None:
-            eng.acquire_device(d_stage, out=(mu, sigma, ei_local), scatter=scatter.scatter_args())
+            eng.acquire_host(h_ca, h_ei_shard, sync=False, scatter=scatter.scatter_args())
             scatter.barrier()
-        else:
+        else:  # --collective nccl: un-pipelined copy, kernels, all-gather, copy of this rank's rows
+            d_stage.copy_(h_ca, non_blocking=True)
             eng.acquire_device(d_stage, out=(mu, sigma, ei_local))
             dist.all_gather_into_tensor(ei_full, ei_local)
-        h_ei.copy_(ei_full, non_blocking=True)
+            h_ei_shard.copy_(ei_local, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
 
     def timed(fn, steps, warmup, flush_l2=True, collective=True):
@@ -293,6 +301,67 @@ def main() -> None:
     ms_post = timed(k_post, args.steps, 3, collective=False)
     clocks.__exit__()
 
+    # Once per model update (every BO step) the evaluated-set state is rebuilt: inverted index, E x E Gram, Cholesky
+    # (cuSOLVER), L^-1 packing, posterior at the evaluated kernels, current_max -- outside `value` and `e2e`, reported here.
+    def engine_build_ms(ev_dev, y_np, reps=7):
+        y_t = torch.from_numpy(y_np)
+        for _ in range(2):
+            sot.AcquisitionEngine(ev_dev, y_t, gram, w, hyp.variance, hyp.lengthscale, hyp.noise_variance, hyp.mean_c)
+        ev_ms, wall_ms = [], []
+        for _ in range(reps):
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a.record()
+            sot.AcquisitionEngine(ev_dev, y_t, gram, w, hyp.variance, hyp.lengthscale, hyp.noise_variance, hyp.mean_c)
+            b.record()
+            torch.cuda.synchronize(dev)
+            wall_ms.append(1e3 * (time.perf_counter() - t0))
+            ev_ms.append(a.elapsed_time(b))
+        return dict(cuda_event_ms=float(np.median(ev_ms)), wall_ms=float(np.median(wall_ms)))
+
+    build_200 = engine_build_ms(d_ev, y) if rank == 0 else None
+
+    # N > 1: the product path of the scaling run is checked in the run itself.  (1) every rank: the vector the fused
+    # scatter left on this GPU == the NCCL all-gather of the per-rank slices, bit for bit; (2) rank 0: 300 random rows
+    # of the whole pool against the CPU oracle (the rows' trees are collected from the ranks that own them).
+    multi_gpu_parity = None
+    if world > 1:
+        from bosot_b200.encoding import decode_to_tuple
+
+        eng.acquire_device(d_ca, out=(mu, sigma, ei_local))
+        gathered = torch.empty(pool, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(gathered, ei_local)
+        same = True
+        if scatter is not None:
+            scatter.values.fill_(float("nan"))
+            scatter.barrier()
+            step_device()
+            torch.cuda.synchronize(dev)
+            same = bool(torch.equal(scatter.values, gathered))
+            h_ei.fill_(float("nan"))
+            step_e2e_multi()
+            same = same and bool(torch.equal(scatter.values, gathered)) and bool(torch.equal(h_ei_shard, gathered[lo:hi].cpu()))
+        flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        idx = np.sort(np.random.default_rng(99).choice(pool, size=300, replace=False))
+        rows = torch.zeros((300, 64), dtype=torch.uint8, device=dev)
+        mine = (idx >= lo) & (idx < hi)
+        if mine.any():
+            rows[torch.from_numpy(np.nonzero(mine)[0]).to(dev)] = d_ca[torch.from_numpy(idx[mine] - lo).to(dev)]
+        dist.all_reduce(rows, op=dist.ReduceOp.SUM)
+        oracle_ok = True
+        if rank == 0:
+            from oracle import ref_numpy as rn_p
+
+            ev_t = [decode_to_tuple(r_, gram) for r_ in ev_np]
+            ca_t = [decode_to_tuple(r_, gram) for r_ in rows.cpu().numpy()]
+            ref = rn_p.acquisition_function(ev_t, y, ca_t, rn_p.Hyper(**H1), GEN, DIM)
+            got = gathered[torch.from_numpy(idx).to(dev)].cpu().numpy()
+            oracle_ok = bool(np.allclose(got, ref["acq"], rtol=1e-6, atol=1e-12))
+        multi_gpu_parity = dict(fused_scatter_equals_all_gather_on_every_rank=bool(int(flag) == 1), oracle_rows_checked=300,
+                                oracle_rows_match=oracle_ok, ok=bool(int(flag) == 1) and oracle_ok)
+
     # fp64 FMA ceiling of this GPU (secondary roofline of the posterior kernel)
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     probe_out = torch.empty(sms * 8 * 256, dtype=torch.float64, device=dev)
@@ -324,9 +393,20 @@ def main() -> None:
         o4 = tuple(torch.empty(C4_POOL, dtype=torch.float64, device=dev) for _ in range(3))
         ms4 = timed(lambda: eng4.acquire_device(d4, out=o4), 20, 5, collective=False)
         ms4_e2e = timed(lambda: eng4.acquire_host(h4, h4_ei, sync=True), 20, 5, collective=False)
+        alg4 = algorithmic_bytes_per_pair(C4_POOL, C4_EVAL) * C4_POOL * C4_EVAL
+        hbm = measured_peaks()["hbm_gbs"]
+        build_50 = engine_build_ms(sot.as_device_trees(ev4, dev), y4)
+        # the reference's native call size: one EA generation of 100 candidates
+        d100 = d4[:100].contiguous()
+        o100 = tuple(torch.empty(100, dtype=torch.float64, device=dev) for _ in range(3))
+        ms100 = timed(lambda: eng4.acquire_device(d100, out=o100), 50, 10, flush_l2=False, collective=False)
         c4 = dict(workload="c4_airfoil_10k_x_50", ms_per_step=ms4, pairs_per_s=C4_POOL * C4_EVAL / (ms4 * 1e-3),
                   ei_candidates_per_s=C4_POOL / (ms4 * 1e-3), e2e_ms=ms4_e2e, e2e_pairs_per_s=C4_POOL * C4_EVAL / (ms4_e2e * 1e-3),
-                  e2e_ei_candidates_per_s=C4_POOL / (ms4_e2e * 1e-3))
+                  e2e_ei_candidates_per_s=C4_POOL / (ms4_e2e * 1e-3),
+                  roofline=dict(bound="hbm", achieved=alg4 / (ms4 * 1e-3) / 1e9, peak=hbm, unit="GB/s", frac=alg4 / (ms4 * 1e-3) / 1e9 / hbm,
+                                algorithmic_bytes_per_step=alg4, note="whole step (all launches); launch latency, not bandwidth, bounds a pool this small"),
+                  engine_build_ms=build_50, e2e_with_update_ms=ms4_e2e + build_50["cuda_event_ms"],
+                  call_100_x_50_device_ms=ms100)
 
     # One BO loop at the shape of BASELINE.json config 4 (Airfoil-shaped: CKSHighDim d = 5, 10k-candidate EA pool per step)
     # through the reference-facing API: model update (ML-II fit on the device) + EA acquisition optimisation per BO step;
@@ -419,13 +499,17 @@ def main() -> None:
     else:  # posterior: K* panel read once, mu/sigma/EI written
         alg_bytes = (8.0 * N_EVAL + 24.0) * n_local
         dur = ms_post
-    traffic = None  # DRAM bytes per launch from the committed ncu capture, only when this run has the same shape
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        if tj.get("n_cand") == n_local and tj.get("n_eval") == N_EVAL and dominant in tj:
-            traffic = tj[dominant]["dram_bytes"]
+    traffic = None  # DRAM bytes from the committed ncu capture, only when this run has the same shape
+    for tname in ("r2_traffic.json", "r1_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj.get("n_cand") == n_local and tj.get("n_eval") == N_EVAL and dominant in tj:
+                traffic = tj[dominant]["dram_bytes"]
+                if dominant == "sot_pair_kernel" and "scan_kernel" in tj:
+                    traffic += tj["scan_kernel"]["dram_bytes"]  # kernel_ms spans both launches of bosot_sot_pairs
+            break
     achieved = alg_bytes / (dur * 1e-3) / 1e9
     post_flops = n_local * (float(N_EVAL) * (N_EVAL + 1) + 4.0 * N_EVAL)  # triangular product + mean + norm
     roofline = dict(
@@ -482,7 +566,9 @@ def main() -> None:
         cpu = dict(value=r["pairs_per_s"], unit="pairs/s", cores=r["cores"], kind="port",
                    sample="first %d candidates of the pool x %d evaluated in %.1f s: %d worker processes, calls of 100 "
                           "candidates; K_diag taken as variance" % (sample, N_EVAL, r["seconds"], r["cores"]),
-                   ei_candidates_per_sec=r["cand_per_s"], gpu_matches_cpu_on_sample=ok)
+                   ei_candidates_per_sec=r["cand_per_s"], gpu_matches_cpu_on_sample=ok, blas_threads_per_worker=1,
+                   pair_distances_computed_per_call=r["pair_distances_computed_per_call"],
+                   pair_distances_credited_per_call=r["pair_distances_credited_per_call"])
 
     if rank == 0:
         line = dict(
@@ -496,9 +582,16 @@ def main() -> None:
             ei_candidates_per_sec=pool / (ms_step * 1e-3),
             clocks=clocks.summary(),
             e2e=dict(value=e2e_value, unit="pairs/s", ms_per_step=ms_e2e, ei_candidates_per_sec=pool / (ms_e2e * 1e-3),
-                     h2d_bytes_per_step=pool * 64, d2h_bytes_per_step=pool * 8 * world,
+                     h2d_bytes_per_step=pool * 64, d2h_bytes_per_step=pool * 8,
                      api="AcquisitionEngine.acquire_host (C-ABI bosot_acquire_host)" if world == 1 else
-                         "pinned H2D + AcquisitionEngine.acquire_device + EI exchange (config.collective) + pinned D2H"),
+                         ("AcquisitionEngine.acquire_host(scatter=...) per rank on its shard (C-ABI bosot_acquire_host_scatter: H2D of "
+                          "the shard | kernels + NVLink scatter | D2H of the shard's EI rows) + 1 symmetric-memory barrier; whole job: "
+                          "the pool in, the pool's EI values out (each rank its rows), the full EI vector on every GPU"
+                          if scatter is not None else
+                          "pinned H2D of the shard + acquire_device + all_gather + pinned D2H of the shard's rows")),
+            engine_build_ms=build_200,
+            e2e_with_update_ms=(ms_e2e + build_200["cuda_event_ms"]) if build_200 else None,
+            multi_gpu_parity=multi_gpu_parity,
             gpu_launches=launches * world,
             roofline=roofline,
             cpu_baseline=cpu,
@@ -509,6 +602,8 @@ def main() -> None:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+        if multi_gpu_parity is not None and not multi_gpu_parity["ok"]:
+            sys.exit("bench: multi-GPU parity check FAILED: %s" % json.dumps(multi_gpu_parity))
 
 
 if __name__ == "__main__":

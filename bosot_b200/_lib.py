@@ -70,6 +70,7 @@ SIGNATURES = {
     "bosot_last_error": (C.c_char_p, []),
     "bosot_abi_version": (C.c_int, []),
     "bosot_shutdown": (C.c_int, []),
+    "bosot_host_pipeline_config": (C.c_int, [C.c_int64, C.c_int64]),
     "bosot_featurize": (C.c_int, [_P, C.c_int64, _G] + [_P] * 11 + [_P]),
     "bosot_eval_state_bytes": (C.c_size_t, [C.c_int]),
     "bosot_eval_build": (C.c_int, [_P, C.c_int, _G, _P, C.c_size_t, _P, _P]),

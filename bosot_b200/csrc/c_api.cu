@@ -121,6 +121,8 @@ struct HostPipe {
   std::mutex mutex;
 };
 static HostPipe g_pipe[kMaxDevices];
+// tuning knobs of the host pipeline (bosot_host_pipeline_config): smallest pool that is chunked, smallest first chunk
+static std::atomic<long long> g_pipe_min_cand{100000}, g_pipe_first_chunk{16384};
 
 static void host_pipe_destroy(HostPipe& P) {
   if (P.h2d) cudaStreamDestroy(P.h2d);
@@ -150,6 +152,13 @@ static int host_pipe_init(HostPipe& P) {
   return BOSOT_OK;
 }
 }  // namespace bosot
+
+extern "C" int bosot_host_pipeline_config(int64_t min_candidates, int64_t first_chunk) {
+  if (min_candidates < 0 || first_chunk < 0) return set_error(BOSOT_EINVAL, "bosot_host_pipeline_config: negative argument");
+  if (min_candidates > 0) g_pipe_min_cand.store(min_candidates, std::memory_order_relaxed);
+  if (first_chunk > 0) g_pipe_first_chunk.store(first_chunk, std::memory_order_relaxed);
+  return BOSOT_OK;
+}
 
 extern "C" int bosot_shutdown(void) {
   int keep = 0;
@@ -248,7 +257,7 @@ static int acquire_from_host(const char* who, const uint8_t* h_trees, int64_t n_
   uint8_t* d_recs = w + W.off_recs;
   const bool want_acq = h_acq != nullptr || d_peers != nullptr;
 
-  if (n_cand < 400000) {
+  if (n_cand < g_pipe_min_cand.load(std::memory_order_relaxed)) {
     // small pool: nothing to overlap, keep everything on the caller's stream (no cross-stream event hops)
     if (int rc = cuda_check(cudaMemcpyAsync(d_trees, h_trees, (size_t)n_cand * kTreeBytes, cudaMemcpyHostToDevice, st), "H2D trees")) return rc;
     if (int rc = launch_pairs(d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale, d_K, nullptr, nullptr, W.ld,
@@ -281,12 +290,16 @@ static int acquire_from_host(const char* who, const uint8_t* h_trees, int64_t n_
   // every chunk three times the one before -- the copy engine delivers trees several times faster than the kernels
   // consume them, so the next, larger chunk is resident before the current one is done -- which keeps the number of
   // launches (and their tails) small.  Measured at 1M x 200: growth 2 / 3 / 4 = 4.22 / 4.19 / 4.26 ms (equal chunks of
-  // 200k behind a quarter-size first chunk: 4.23 ms).
+  // 200k behind a quarter-size first chunk: 4.23 ms).  Round 2 (profiles/r2c_pipe.log): shards of 125k / 250k / 500k candidates
+  // (the 8 / 4 / 2-GPU runs) un-chunked 1.33 / 1.45 / 2.73 ms, chunked from 100k up with a first chunk of >= 16384 candidates
+  // 0.77 / 1.17 / 2.21 ms (first chunk 8192: 0.94 ms at 125k -- too many small launches).
   constexpr int kGrow = 3;
   int64_t bounds[kMaxChunks + 1];
   int n_parts = 0;
   {
-    int64_t len = ((n_cand / 20) + 63) & ~(int64_t)63, c = 0;
+    const int64_t first = g_pipe_first_chunk.load(std::memory_order_relaxed);
+    int64_t len = n_cand / 20 > first ? n_cand / 20 : first, c = 0;
+    len = (len + 63) & ~(int64_t)63;
     while (c < n_cand && n_parts < kMaxChunks - 1) {
       bounds[n_parts++] = c;
       c += len;

@@ -39,7 +39,7 @@
  * exits.  One call in flight per stream.
  * State: none besides caller-owned buffers, with ONE exception -- bosot_acquire_host /
  * bosot_acquire_host_scatter keep, per device, three helper streams and a few events for their
- * chunked copy/compute pipeline (created on the first call with >= 400000 candidates on that
+ * chunked copy/compute pipeline (created on the first call with >= 100000 candidates on that
  * device, guarded by a per-device mutex that is held only while work is ENQUEUED, released by
  * bosot_shutdown()).
  * fp64 throughout ("f64" path); the reference computes in float64 as well
@@ -104,6 +104,10 @@ int bosot_abi_version(void);
 /* Synchronises and destroys the helper streams / events of the host-buffer pipeline on every device (see "State"
  * above).  Optional; the library can be used again afterwards (the pipeline is rebuilt on demand). */
 int bosot_shutdown(void);
+/* Tuning knobs of that pipeline (process-wide; 0 keeps a value): pools of fewer than min_candidates candidates run
+ * un-chunked on the caller's stream (default 100000); the first chunk holds max(n_cand / 20, first_chunk) candidates
+ * (default 16384), every later chunk three times the one before. */
+int bosot_host_pipeline_config(int64_t min_candidates, int64_t first_chunk);
 
 /* ---- featurisation (ordered sparse histograms) ---------------------------------
  * Per tree i (all arrays row-major, caller-allocated on the device):
@@ -197,7 +201,7 @@ int bosot_max_f64(const double* d_x, int64_t n, double* d_out, void* stream);
 /* ---- host-buffer convenience (the end-to-end call) --------------------------------------
  * Candidates in (preferably pinned) host memory -> acquisition values in host memory.
  * Copies h_trees into d_work, runs pairs + posterior, copies acq (and mu/sigma when non-NULL) back, ordered
- * on `stream`; the caller synchronises the stream.  Pools of >= 400000 candidates flow through a chunked
+ * on `stream`; the caller synchronises the stream.  Pools of >= 100000 candidates flow through a chunked
  * H2D | kernels | D2H pipeline on helper streams that is joined back into `stream` before the call returns
  * (also when it returns an error); with pageable host memory the copies (and so the call) block.
  * d_work: device scratch of bosot_acquire_work_bytes(n_cand, n_eval) bytes.
