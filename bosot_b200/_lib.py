@@ -99,6 +99,7 @@ SIGNATURES = {
         [_P, C.c_int64, _G, _P, C.c_int, _D3, C.c_double, C.c_double, _P, C.c_int, _P, C.c_double, C.c_int, _P, C.c_double, C.c_double,
          _P, C.c_size_t, _P, _P, _P, _P, _P, C.c_int, C.c_int64, _P],
     ),
+    "bosot_enable_peer_access": (C.c_int, [C.c_int]),
     "bosot_posterior_acq_scatter": (
         C.c_int,
         [_P, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, _P, C.c_double, C.c_double, C.c_int, _P, C.c_double, C.c_double, _P, _P, _P,
@@ -109,6 +110,10 @@ SIGNATURES = {
         [_P, C.c_int64, _G, _P, C.c_int, _D3, C.c_double, C.c_double, _P, C.c_int, _P, C.c_double, C.c_int, _P, C.c_double, C.c_double,
          _P, C.c_size_t, _P, _P, _P, _P, _P, C.c_int, C.c_int64, _P],
     ),
+    "bosot_topk_work_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "bosot_topk_f64": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, C.c_size_t, _P]),
+    "bosot_argmax_work_bytes": (C.c_size_t, []),
+    "bosot_argmax_f64": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, C.c_size_t, _P]),
     "bosot_neighbours": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P, _P]),
     "bosot_host_choices": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
     "bosot_host_recursive_dataset": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, C.c_int, _P, C.POINTER(C.c_int64)]),

@@ -33,7 +33,11 @@ class EvolutionaryOptimizerObjects:
         return self.current_maximizer, self.current_maximizer_value
 
     def select(self, population, function_values):
-        order = np.argsort(function_values)
+        # stable: equal acquisition values (duplicates in the population, commuted children) keep their population
+        # order.  The reference calls np.argsort with the default kind, whose order of EQUAL values depends on the
+        # NumPy build (introsort or the AVX-512 sorter); the stable order is the portable reading, and it is what the
+        # device-side selection of the flat EA (bosot_topk_f64) implements.
+        order = np.argsort(function_values, kind="stable")
         n_survive = int(self.population_size * self.survival_rate)
         return [population[i] for i in order[len(order) - n_survive :]]
 

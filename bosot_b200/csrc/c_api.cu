@@ -153,6 +153,17 @@ static int host_pipe_init(HostPipe& P) {
 }
 }  // namespace bosot
 
+extern "C" int bosot_enable_peer_access(int peer_device) {
+  int dev = 0, can = 0;
+  if (int rc = cuda_check(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+  if (peer_device == dev) return BOSOT_OK;
+  if (int rc = cuda_check(cudaDeviceCanAccessPeer(&can, dev, peer_device), "cudaDeviceCanAccessPeer")) return rc;
+  if (!can) return set_error(BOSOT_EINVAL, "bosot_enable_peer_access: the current device cannot map the peer's memory");
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return BOSOT_OK; }
+  return cuda_check(e, "cudaDeviceEnablePeerAccess");
+}
+
 extern "C" int bosot_host_pipeline_config(int64_t min_candidates, int64_t first_chunk) {
   if (min_candidates < 0 || first_chunk < 0) return set_error(BOSOT_EINVAL, "bosot_host_pipeline_config: negative argument");
   if (min_candidates > 0) g_pipe_min_cand.store(min_candidates, std::memory_order_relaxed);

@@ -161,24 +161,34 @@ class FlatEvolutionaryOptimizer:
         self.current_maximizer_value = -np.inf
 
     def maximize(self, func: Callable[[torch.Tensor], torch.Tensor], steps: int):
-        """``func`` maps a device tensor of flat records to a device tensor of acquisition values."""
+        """``func`` maps a device tensor of flat records to a device tensor of acquisition values.
+
+        Selection runs on the device (``sot.topk`` = the tail of the stable argsort, ``sot.argmax_first`` = np.argmax):
+        per generation only the survivors' node-count bytes and 16 bytes of (best value, best index) go to the host,
+        and the drawn (parent, neighbour number) pairs come back -- the acquisition vector never crosses PCIe."""
+        from . import sot
+
         gen = self.generator
         population = torch.from_numpy(gen.get_initial_for_evolutionary_opt(self.population_size)).to(self.device)
         values = None
         for step in range(steps):
             if step > 0:
-                order = np.argsort(values)  # host argsort: the reference's tie-breaking, 8 bytes per candidate
                 n_survive = int(self.population_size * self.survival_rate)
-                surv_idx = order[len(order) - n_survive:]
-                survivors = population[torch.from_numpy(surv_idx).to(self.device)]
-                parent, index = gen.draw_offspring_indices(survivors.cpu().numpy(), self.num_offspring)
+                if n_survive > 0:
+                    surv_idx, _ = sot.topk(values, n_survive, want_values=False)  # ascending by (value, index), like the stable argsort
+                    survivors = population[surv_idx]
+                else:
+                    survivors = population[:0]
+                # the host draws the neighbour numbers (np.random replay); it needs the node count of every survivor only
+                parent, index = gen.draw_offspring_indices(survivors[:, :1].cpu().numpy(), self.num_offspring)
                 offspring = neighbours_device(survivors[torch.from_numpy(parent).to(self.device)].contiguous(),
                                               torch.from_numpy(index), gen.grammar)
                 population = torch.cat([offspring, survivors])
-            values = func(population).cpu().numpy()
-            fittest = int(np.argmax(values))
-            if self.current_maximizer_value < values[fittest]:
-                self.current_maximizer_value = float(values[fittest])
+            values = func(population).contiguous()
+            best = sot.argmax_first(values).cpu().numpy()
+            fittest = int(best[1])
+            if self.current_maximizer_value < best[0]:
+                self.current_maximizer_value = float(best[0])
                 self.current_maximizer = population[fittest].cpu().numpy()
         return self.current_maximizer, self.current_maximizer_value
 

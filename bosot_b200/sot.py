@@ -247,6 +247,44 @@ def max_f64(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# ------------------------------------------------------------- selection on the device
+def topk(values: torch.Tensor, k: int, index_offset: int = 0, want_values: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """The last ``k`` entries of ``np.argsort(values, kind="stable")`` without leaving the device (C-ABI
+    ``bosot_topk_f64``): what ``EvolutionaryOptimizerObjects.select`` keeps (evolutionary_optimizer_objects.py:57-64).
+    Returns (int64 indices + ``index_offset``, their values), ascending by (value, index); NaN sorts last like NumPy."""
+    _need_cuda(values, "values")
+    if values.dtype != torch.float64 or values.dim() != 1 or not values.is_contiguous():
+        raise ValueError("topk takes a contiguous 1-D float64 tensor")
+    lib = _lib.load()
+    n, dev = values.numel(), values.device
+    k = int(k)
+    if not (1 <= k <= n):
+        raise ValueError("topk needs 1 <= k <= n")
+    idx = torch.empty(k, dtype=torch.int64, device=dev)
+    vals = torch.empty(k, dtype=torch.float64, device=dev) if want_values else None
+    nbytes = lib.bosot_topk_work_bytes(n, k)
+    work = torch.empty(max(16, nbytes), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.bosot_topk_f64(values.data_ptr(), n, k, int(index_offset), idx.data_ptr(), _ptr(vals), work.data_ptr(), work.numel(), _stream(dev))
+    _lib.check(rc, "topk")
+    return idx, vals
+
+
+def argmax_first(values: torch.Tensor, index_offset: int = 0) -> torch.Tensor:
+    """``np.argmax`` on the device (C-ABI ``bosot_argmax_f64``): float64 [2] = (max value, its FIRST index + offset)."""
+    _need_cuda(values, "values")
+    if values.dtype != torch.float64 or values.dim() != 1 or not values.is_contiguous() or values.numel() < 1:
+        raise ValueError("argmax_first takes a non-empty contiguous 1-D float64 tensor")
+    lib = _lib.load()
+    dev = values.device
+    out = torch.empty(2, dtype=torch.float64, device=dev)
+    work = torch.empty(lib.bosot_argmax_work_bytes(), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.bosot_argmax_f64(values.data_ptr(), values.numel(), int(index_offset), out.data_ptr(), work.data_ptr(), work.numel(), _stream(dev))
+    _lib.check(rc, "argmax")
+    return out
+
+
 # ------------------------------------------------------------------------ composed engine
 class AcquisitionEngine:
     """Everything that depends on the evaluated set and the hyper-parameters, prepared once per

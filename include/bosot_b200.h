@@ -26,6 +26,8 @@
  *   bosot_acquire_host / _device  the whole acquisition_function call (same file, :159-168) on flat trees
  *   bosot_*_scatter ........... the same for a pool that is row-sharded over the GPUs of one node (no reference
  *                               counterpart: the reference is single-process)
+ *   bosot_topk_f64, bosot_argmax_f64  EvolutionaryOptimizerObjects.select / np.argmax on the device
+ *                               (bayesian_optimization/evolutionary_optimizer_objects.py:42-44,57-64)
  *   bosot_gp_nll_grad ......... GPR.training_loss + gradient for the ML-II fit (models/gp_model.py:162-199)
  *   bosot_neighbours, bosot_host_choices, bosot_host_recursive_dataset
  *                               the candidate producers (kernels/kernel_grammar/kernel_grammar_search_spaces.py:97-151,
@@ -237,6 +239,9 @@ int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, const bosot_gra
  * (NVLink / NVSwitch P2P, e.g. a torch symmetric-memory allocation); peer_offset = first global row of this shard.
  * d_acq (the local copy) is still written and must not be NULL.  The caller orders the buffers with a cross-GPU
  * barrier after the call (symmetric-memory barrier) before any rank reads its vector. */
+/* Maps the memory of peer_device into the current device (cudaDeviceEnablePeerAccess; "already enabled" is not an
+ * error), for callers that allocate the peer vectors themselves instead of through a symmetric-memory allocator. */
+int bosot_enable_peer_access(int peer_device);
 int bosot_posterior_acq_scatter(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval,
                                 const double* d_LinvF, int ldl, const double* d_beta, double mean_c, double variance,
                                 int acq_kind, const double* d_current_max, double xi, double ucb_beta,
@@ -261,6 +266,22 @@ int bosot_acquire_host_scatter(const uint8_t* h_trees, int64_t n_cand, const bos
                                void* d_work, size_t work_bytes,
                                double* h_mu, double* h_sigma, double* h_acq, int32_t* h_n_bad,
                                const void* d_peer_ptrs, int n_peers, int64_t peer_offset, void* stream);
+
+/* ---- device-side selection for the evolutionary optimiser -------------------------
+ * EvolutionaryOptimizerObjects.select keeps the last k = int(pop / (offspring + 1)) entries of np.argsort(values)
+ * (bayesian_optimization/evolutionary_optimizer_objects.py:57-64) and maximize takes np.argmax (:42-44).
+ * bosot_topk_f64: d_out_index[j] (int64, + index_offset) / d_out_value[j] (may be NULL), j = 0 .. k-1, are the last k
+ * entries of the ascending order by (value, index) = np.argsort(values, kind="stable")[n-k:]; NaN sorts above +inf
+ * like NumPy, -0.0 == +0.0.  1 <= k <= n < 2^31.  d_work: bosot_topk_work_bytes(n, k) bytes, 16-byte aligned
+ * (not touched when n <= 16384: one CTA sorts in shared memory).  No host synchronisation.
+ * bosot_argmax_f64: d_out2[0] = max value, d_out2[1] = its FIRST index (+ index_offset) as a double (np.argmax: a NaN
+ * counts as the maximum).  d_work: bosot_argmax_work_bytes() bytes (used when n > 65536). */
+size_t bosot_topk_work_bytes(int64_t n, int64_t k);
+int bosot_topk_f64(const double* d_values, int64_t n, int64_t k, int64_t index_offset, int64_t* d_out_index,
+                   double* d_out_value, void* d_work, size_t work_bytes, void* stream);
+size_t bosot_argmax_work_bytes(void);
+int bosot_argmax_f64(const double* d_values, int64_t n, int64_t index_offset, double* d_out2, void* d_work,
+                     size_t work_bytes, void* stream);
 
 /* ---- hyper-parameter fit of the GP over kernels ----------------------------------
  * One launch = one evaluation of GPR's training loss (negative log marginal likelihood; reference
