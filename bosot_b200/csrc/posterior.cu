@@ -81,6 +81,7 @@ posterior_kernel(PostParams p) {
   int* work = reinterpret_cast<int*>(mus + kPostCand);       // shared work counter
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
+  pdl_wait();  // K* may come from the launch directly in front of this one
 
   for (int64_t tile = blockIdx.x; tile * kPostCand < p.n_cand; tile += gridDim.x) {
     const int64_t c0 = tile * kPostCand;
@@ -273,6 +274,7 @@ posterior_ws_kernel(PostParams p) {
   for (int x = threadIdx.x; x < (int)((W.total - W.off_ks) / sizeof(double)); x += kWsThreads) Ks[x] = 0.0;  // everything finite
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");             // generic-proxy zeros before async-proxy writes
   __syncthreads();
+  pdl_wait();  // everything above overlapped the tail of the launch in front (the pair kernel); K* is complete from here on
 
   // one warp issues the TMA row copies of this CTA's tile number i into stage i & 1 (every lane its share of the rows)
   const uint32_t row_bytes = (uint32_t)((E + 1) & ~1) * 8u;  // whole 16-byte units; for odd E one (finite) padding column comes along
@@ -632,22 +634,26 @@ int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_ev
                               "cudaFuncSetAttribute(posterior_ws_kernel<16>)")) return rc;
       if (dev < 64) ws_attr[dev] = true;
     }
-    const size_t s64 = ws_layout<64>(n_eval).total, s32 = ws_layout<32>(n_eval).total;
-    if (s64 <= smem_cap) {
-      const int64_t tiles = (n_cand + 63) / 64;
-      posterior_ws_kernel<64><<<(unsigned)(tiles < sms ? tiles : sms), kWsThreads, s64, stream>>>(p);
-      return after_launch("posterior_ws_kernel<64>");
-    }
-    if (s32 <= smem_cap) {
-      const int64_t tiles = (n_cand + 31) / 32;
-      posterior_ws_kernel<32><<<(unsigned)(tiles < sms ? tiles : sms), kWsThreads, s32, stream>>>(p);
-      return after_launch("posterior_ws_kernel<32>");
-    }
-    const size_t s16 = ws_layout<16>(n_eval).total;
-    if (s16 <= smem_cap) {
-      const int64_t tiles = (n_cand + 15) / 16;
-      posterior_ws_kernel<16><<<(unsigned)(tiles < sms ? tiles : sms), kWsThreads, s16, stream>>>(p);
-      return after_launch("posterior_ws_kernel<16>");
+    // Tile width: 64 candidates per CTA tile is the efficient shape (every A fragment of L^-1 feeds 16 DMMAs), but a
+    // small pool must still put work on every SM: take the widest tile that fits shared memory and still gives every
+    // SM two tiles, else the narrowest one (10k candidates: 313 tiles of 32; the reference's own call size of 100
+    // candidates: 7 tiles of 16 instead of 2 of 64).
+    const size_t smem_tc[3] = {ws_layout<64>(n_eval).total, ws_layout<32>(n_eval).total, ws_layout<16>(n_eval).total};
+    const int width[3] = {64, 32, 16};
+    int pick = -1;
+    for (int i = 0; i < 3 && pick < 0; ++i)
+      if (smem_tc[i] <= smem_cap && (n_cand + width[i] - 1) / width[i] >= 2LL * sms) pick = i;
+    for (int i = 2; i >= 0 && pick < 0; --i)
+      if (smem_tc[i] <= smem_cap) pick = i;
+    if (pick >= 0) {
+      const int64_t tiles = (n_cand + width[pick] - 1) / width[pick];
+      const dim3 grid((unsigned)(tiles < sms ? tiles : sms)), block(kWsThreads);
+      cudaError_t e = cudaSuccess;
+      if (pick == 0) e = launch_pdl(posterior_ws_kernel<64>, grid, block, smem_tc[0], stream, p);
+      else if (pick == 1) e = launch_pdl(posterior_ws_kernel<32>, grid, block, smem_tc[1], stream, p);
+      else e = launch_pdl(posterior_ws_kernel<16>, grid, block, smem_tc[2], stream, p);
+      if (int rc = cuda_check(e, "cudaLaunchKernelEx(posterior_ws_kernel)")) return rc;
+      return after_launch("posterior_ws_kernel");
     }
   }
 
@@ -667,7 +673,7 @@ int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_ev
   const int64_t tiles = (n_cand + kPostCand - 1) / kPostCand;
   const int64_t wave = (int64_t)sms * per_sm;
   const int64_t grid = tiles < wave ? tiles : wave;
-  posterior_kernel<<<(unsigned)grid, kPostThreads, smem, stream>>>(p);
+  if (int rc = cuda_check(launch_pdl(posterior_kernel, dim3((unsigned)grid), dim3(kPostThreads), smem, stream, p), "cudaLaunchKernelEx(posterior_kernel)")) return rc;
   return after_launch("posterior_kernel");
 }
 

@@ -147,6 +147,7 @@ __global__ void __launch_bounds__(kScanThreads)
 scan_kernel(const uint8_t* __restrict__ trees, int64_t n_trees, int n_symbols, uint8_t* __restrict__ recs_out,
             int32_t* __restrict__ status, unsigned long long* __restrict__ next, int32_t* __restrict__ bad_zero) {
   extern __shared__ __align__(16) uint8_t smem[];
+  pdl_launch_dependents();  // the pair launch may stage its tables while the scan runs (it waits before reading the records)
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     *next = 0ULL;  // work counter of the pair launch that follows on the stream
     if (bad_zero) *bad_zero = 0;  // ... and its count of malformed records
@@ -256,7 +257,9 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   const unsigned full = 0xffffffffu;
   const unsigned lt_mask = (1u << lane) - 1u, le_mask = (2u << lane) - 1u;
 
+  pdl_launch_dependents();  // a posterior launch behind this one may set up its shared memory early (it waits before reading K*)
   // ---- stage the evaluated set's dense tables once per (persistent) CTA: TMA bulk copies -> mbarrier
+  // (the blob is the product of an OLDER launch than the scan in front of this one, so this may run before pdl_wait())
   const StageLayout S = stage_layout(e_pad, g.n_dim_cols, g.n_symbols, g.n_blocks);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   if (threadIdx.x == 0) mbar_init(bar, 1);
@@ -319,15 +322,17 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     return s;
   };
 
-  // Candidates are claimed one at a time from a global counter, one claim ahead of the work: trees differ in cost by an
-  // order of magnitude (1 .. 63 nodes), and with a static stride the warp with the unluckiest share decided when the
-  // kernel ended (about 240 candidates per warp at 1 M, 30 at 125 k per GPU).
-  auto claim = [&]() {
-    unsigned long long v = 0ULL;
-    if (lane == 0) v = atomicAdd(p.next, 1ULL);
-    return (int64_t)__shfl_sync(full, v, 0);
-  };
-  int64_t t = claim();
+  // Work distribution.  Trees differ in cost by an order of magnitude (1 .. 63 nodes), and with a static stride the warp
+  // with the unluckiest share decided when the kernel ended, so candidates are claimed one at a time from a global
+  // counter -- but never waited for: every warp starts on two candidates it owns by position (its index in the grid
+  // and that plus the number of warps: no atomic on the way to the first tree, which at small pools was a stampede of
+  // thousands of warps on one address, 30 % of all stall samples at 10k candidates), and the claim issued at the top of
+  // iteration i is only read at its end, as the index of candidate i + 2 (its record is prefetched during iteration
+  // i + 1).  The counter hands out the positions from 2 W on.
+  const int64_t n_warps_grid = (int64_t)gridDim.x * n_warps;
+  pdl_wait();  // the scan launch has completed: work counter zeroed, compact records visible
+  int64_t t = (int64_t)blockIdx.x + (int64_t)gridDim.x * warp;  // neighbouring warps of a CTA take trees far apart
+  int64_t t1 = t + n_warps_grid;
   Slice nxt;
   if (t < p.n_cand) nxt = load_slice(t);
   mbar_wait(bar, 0);  // tables landed (the copy overlapped the first record load)
@@ -336,10 +341,11 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
 
 #pragma unroll 1
   for (int e = 2 * lane; e < e_pad; e += 64) *reinterpret_cast<uint2*>(acc + e) = make_uint2(0u, 0u);
-  for (int64_t t_next; t < p.n_cand; t = t_next) {
+  unsigned long long pending = 0ULL;
+  for (; t < p.n_cand; t = t1, t1 = 2 * n_warps_grid + (int64_t)__shfl_sync(full, pending, 0)) {
     const Slice cur = nxt;
-    t_next = claim();
-    if (t_next < p.n_cand) nxt = load_slice(t_next);  // prefetch behind this tree's work
+    if (lane == 0) pending = atomicAdd(p.next, 1ULL);  // candidate after next; consumed by the loop increment
+    if (t1 < p.n_cand) nxt = load_slice(t1);           // prefetch the next record behind this tree's work
 
     const int nn = cur.meta & 0xff, nl = (cur.meta >> 8) & 0xff, ni = (cur.meta >> 16) & 0xff;
     const bool bad = (cur.meta >> 24) != 0;
@@ -668,7 +674,7 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   const int64_t want = (n_cand + warps - 1) / warps;
   const int64_t wave = (int64_t)sms * per_sm;
   const int64_t grid = want < wave ? want : wave;
-  kernel<<<(unsigned)grid, warps * 32, smem, stream>>>(p, *grammar);
+  if (int rc = cuda_check(launch_pdl(kernel, dim3((unsigned)grid), dim3(warps * 32), smem, stream, p, *grammar), "cudaLaunchKernelEx(sot_pair_kernel)")) return rc;
   return after_launch("sot_pair_kernel");
 }
 
