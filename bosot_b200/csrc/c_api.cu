@@ -29,6 +29,15 @@ int after_launch(const char* kernel_name) {
   return cuda_check(cudaGetLastError(), kernel_name);
 }
 
+bool pdl_enabled() {
+  static const bool on = std::getenv("BOSOT_NO_PDL") == nullptr;
+  return on;
+}
+int experiment_flag() {  // BOSOT_EXPERIMENT=<int>: measurement switches of kernels under development (0 = product path)
+  static const int v = std::getenv("BOSOT_EXPERIMENT") ? std::atoi(std::getenv("BOSOT_EXPERIMENT")) : 0;
+  return v;
+}
+
 int check_grammar(const bosot_grammar* g) {
   if (g->n_symbols < 1 || g->n_symbols > BOSOT_MAX_SYMBOLS) return set_error(BOSOT_EINVAL, "grammar: n_symbols out of range");
   if (g->n_blocks < 1 || g->n_blocks > BOSOT_MAX_BLOCKS) return set_error(BOSOT_EINVAL, "grammar: n_blocks out of range");

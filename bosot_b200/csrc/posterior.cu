@@ -620,6 +620,7 @@ int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_ev
   if (int rc = cuda_check(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
   if (int rc = cuda_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return rc;
   const size_t smem_cap = 226 * 1024;
+  const bool early = n_cand <= 32768;  // programmatic dependent launch only where launch latency matters (see launch_pairs)
 
   // warp-specialised TMA variant: needs 16-byte aligned rows of whole 16-byte units
   const bool tma_ok = (ld % 2 == 0) && (n_eval % 2 == 0 || ld > n_eval) && !(reinterpret_cast<uintptr_t>(d_Kstar) & 15);
@@ -649,9 +650,9 @@ int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_ev
       const int64_t tiles = (n_cand + width[pick] - 1) / width[pick];
       const dim3 grid((unsigned)(tiles < sms ? tiles : sms)), block(kWsThreads);
       cudaError_t e = cudaSuccess;
-      if (pick == 0) e = launch_pdl(posterior_ws_kernel<64>, grid, block, smem_tc[0], stream, p);
-      else if (pick == 1) e = launch_pdl(posterior_ws_kernel<32>, grid, block, smem_tc[1], stream, p);
-      else e = launch_pdl(posterior_ws_kernel<16>, grid, block, smem_tc[2], stream, p);
+      if (pick == 0) e = launch_pdl(early, posterior_ws_kernel<64>, grid, block, smem_tc[0], stream, p);
+      else if (pick == 1) e = launch_pdl(early, posterior_ws_kernel<32>, grid, block, smem_tc[1], stream, p);
+      else e = launch_pdl(early, posterior_ws_kernel<16>, grid, block, smem_tc[2], stream, p);
       if (int rc = cuda_check(e, "cudaLaunchKernelEx(posterior_ws_kernel)")) return rc;
       return after_launch("posterior_ws_kernel");
     }
@@ -673,7 +674,7 @@ int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_ev
   const int64_t tiles = (n_cand + kPostCand - 1) / kPostCand;
   const int64_t wave = (int64_t)sms * per_sm;
   const int64_t grid = tiles < wave ? tiles : wave;
-  if (int rc = cuda_check(launch_pdl(posterior_kernel, dim3((unsigned)grid), dim3(kPostThreads), smem, stream, p), "cudaLaunchKernelEx(posterior_kernel)")) return rc;
+  if (int rc = cuda_check(launch_pdl(early, posterior_kernel, dim3((unsigned)grid), dim3(kPostThreads), smem, stream, p), "cudaLaunchKernelEx(posterior_kernel)")) return rc;
   return after_launch("posterior_kernel");
 }
 

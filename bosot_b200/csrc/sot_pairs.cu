@@ -36,9 +36,12 @@
 
 namespace bosot {
 
+int experiment_flag();
+
 constexpr int kMaxPairWarps = 28;   // one persistent CTA of up to 28 warps per SM (72 registers per thread; measured: 20 / 24 / 28 / 32 warps = 2.68 / 2.52 / 2.43 / 2.49 ms)
 constexpr int kScanThreads = 128;
 constexpr int kMaxR = 8;            // evaluated trees per lane per register tile (E <= 256 in one pass, else tiles of 256)
+constexpr int64_t kFusedScanMax = 32768;  // pools up to this size take the fused-scan path (no scan launch)
 
 // Small tables, initialised STATICALLY (constant-folded by the host compiler, so correctly rounded like Python's
 // float(a) / float(b)): nothing is uploaded at run time, hence nothing to order against the caller's stream.
@@ -70,19 +73,28 @@ struct PairParams {
   const uint8_t* recs;  // compact records written by scan_kernel: [n_cand][kScanBytes]
   unsigned long long* next;  // work counter (zeroed by the scan launch): the warps claim candidates one at a time
   int32_t* bad;              // optional: number of malformed candidate records met (their rows are poisoned)
+  int flags;                 // experiment switches (0 = product path)
+  int32_t* status;           // fused-scan path only: per-tree defect codes (may be null)
+  int n_symbols;
 };
 
 // per-warp shared memory: candidate dim-wise vector, block-state distance table, walk segments, accumulators, symbol counts
 struct WarpLayout {
-  size_t off_tab, off_slot, off_acc, off_scnt, total;
+  size_t off_tab, off_slot, off_acc, off_scnt, off_scan, total;
 };
-__host__ __device__ inline WarpLayout warp_layout(int e_pad, int n_dim_cols, int n_blocks) {
+// scratch of the warp-cooperative scan (fused-scan path): idpos u64[64] | lvl_lo u32[34] | lvl_hi u32[34] | oprec u32[32] |
+// endcnt u32[64] | leafrec u16[32]; the cold path (malformed record) reuses it as one scan_tree() working record
+constexpr int kWsIdpos = 0, kWsLvlLo = 512, kWsLvlHi = 648, kWsOprec = 784, kWsEndcnt = 912, kWsLeafrec = 1168, kWarpScanBytes = 1232;
+static_assert(kWarpScanBytes >= kRecBytes, "the cold path runs scan_tree() in the same scratch");
+__host__ __device__ inline WarpLayout warp_layout(int e_pad, int n_dim_cols, int n_blocks, bool fused_scan = false) {
   WarpLayout W;
   size_t o = sizeof(double) * (size_t)((n_dim_cols + 1) & ~1);           // avec [n_pcols]
   W.off_tab = o;   o += sizeof(double) * (size_t)kMaxStates * n_blocks;  // tab [n_blocks][kMaxStates]
   W.off_slot = o;  o += sizeof(uint2) * 32;                              // segments of the flattened postings walk
   W.off_acc = o;   o += sizeof(uint32_t) * (size_t)e_pad;                // M_sub(ops) | M_path << 16 per e
   W.off_scnt = o;  o += sizeof(uint32_t) * (BOSOT_MAX_SYMBOLS + BOSOT_MAX_BLOCKS);
+  o = align16(o);
+  W.off_scan = o;  o += fused_scan ? kWarpScanBytes : 0;
   W.total = align16(o);
   return W;
 }
@@ -203,6 +215,182 @@ scan_kernel(const uint8_t* __restrict__ trees, int64_t n_trees, int n_symbols, u
   }
 }
 
+// ---- warp-cooperative scan of ONE tree (fused-scan path of small pools) ---------------------------------------
+// scan_kernel is a chain of ~2000 dependent shared-memory operations per warp whatever the pool size (17 us at 10k
+// candidates, a third of the whole step); a pool that small cannot fill the machine anyway, so here the 32 lanes of
+// the warp that owns a candidate split its token positions (lane l: positions l and l + 32) and everything except the
+// class ids is closed form on 64-bit position masks.  With w = +1 for an operator and -1 for a leaf and S[p] the
+// inclusive prefix sum of w over the pre-order tokens (S[-1] = 0):
+//   * the record is a tree iff S[p] >= 0 for p < n - 1 and S[n - 1] = -1;
+//   * the subtree that starts at x ends at the first q >= x with S[q] = S[x - 1] - 1, so the right child of the operator
+//     at p is 1 + (first q > p with S[q] = S[p] - 1);
+//   * the parent of p is p - 1 if that is an operator, else the nearest operator b < p with S[b] = S[p - 1] + 1;
+//   * an operator "changes" when it is the root or differs from its parent's operator; the reduced path of a leaf has
+//     as many runs as it has changing ancestors = (changing operators before it) - (changing operators whose subtree
+//     ended before it), and its nearest operator is its parent's  (reduce_operator_list, kernel_grammar.py:649-658).
+// "First / nearest position with S = v" is one bit scan on the mask of positions of level v (match_any groups).
+// Class ids go bottom-up: operator number r (pre-order rank) lives on lane r and fires once both children are ready.
+// Any record the closed form rejects is handed to scan_tree() on lane 0, which yields the exact defect code.
+struct Slice { unsigned long long id; uint32_t meta, sym, code; };
+struct RawTree { uint32_t n, tk0, tk1; };
+
+__device__ __forceinline__ RawTree load_raw(const uint8_t* __restrict__ rec, int lane) {
+  RawTree r;
+  r.n = __ldg(rec);
+  r.tk0 = __ldg(rec + 1 + lane);
+  r.tk1 = lane < 31 ? (uint32_t)__ldg(rec + 33 + lane) : (uint32_t)BOSOT_PAD;
+  return r;
+}
+
+__device__ __forceinline__ unsigned long long mask_below(int p) { return p >= 64 ? ~0ULL : (1ULL << p) - 1ULL; }  // positions < p
+
+__device__ __forceinline__ Slice warp_scan_tree(const RawTree raw, const uint8_t* __restrict__ rec_global, int n_symbols,
+                                                uint8_t* scratch, int lane) {
+  const unsigned full = 0xffffffffu;
+  const int n = (int)raw.n;
+  const int p0 = lane, p1 = lane + 32;
+  const bool len_ok = n >= 1 && n <= kMaxNodes && (n & 1);
+  const bool v0 = len_ok && p0 < n, v1 = len_ok && p1 < n;
+  const uint32_t tk0 = raw.tk0, tk1 = raw.tk1;
+  const bool op0 = v0 && tk0 >= 0x80u, op1 = v1 && tk1 >= 0x80u;
+  const bool bt0 = v0 && (tk0 >= 0x80u ? tk0 > (uint32_t)BOSOT_OP_MUL : (int)tk0 >= n_symbols);
+  const bool bt1 = v1 && (tk1 >= 0x80u ? tk1 > (uint32_t)BOSOT_OP_MUL : (int)tk1 >= n_symbols);
+  const unsigned long long opmask = (unsigned long long)__ballot_sync(full, op0) | ((unsigned long long)__ballot_sync(full, op1) << 32);
+  const unsigned long long mulmask = (unsigned long long)__ballot_sync(full, op0 && tk0 == (uint32_t)BOSOT_OP_MUL) |
+                                     ((unsigned long long)__ballot_sync(full, op1 && tk1 == (uint32_t)BOSOT_OP_MUL) << 32);
+  const int s0 = 2 * __popcll(opmask & mask_below(p0 + 1)) - (p0 + 1);
+  const int s1 = 2 * __popcll(opmask & mask_below(p1 + 1)) - (p1 + 1);
+  const bool sb0 = v0 && (p0 == n - 1 ? s0 != -1 : s0 < 0);
+  const bool sb1 = v1 && (p1 == n - 1 ? s1 != -1 : s1 < 0);
+  Slice out;
+  if (!len_ok || __ballot_sync(full, bt0 | bt1 | sb0 | sb1) != 0u) {
+    // cold path: the sequential scan decides (and names the defect); the slice is read back from its working record
+    __syncwarp();
+    if (lane < 16) reinterpret_cast<uint32_t*>(scratch + kRecTok)[lane] = __ldg(reinterpret_cast<const uint32_t*>(rec_global) + lane);
+    __syncwarp();
+    if (lane == 0) scan_tree(scratch, n_symbols);
+    __syncwarp();
+    out.meta = *reinterpret_cast<const uint32_t*>(scratch + kRecMeta);
+    out.id = lane < kMaxInternal ? reinterpret_cast<const unsigned long long*>(scratch + kRecIid)[lane] : 0ULL;
+    out.sym = scratch[kRecLeafSym + lane];
+    out.code = scratch[kRecLeafCode + lane];
+    __syncwarp();
+    return out;
+  }
+  unsigned long long* idpos = reinterpret_cast<unsigned long long*>(scratch + kWsIdpos);
+  uint32_t* lvl_lo = reinterpret_cast<uint32_t*>(scratch + kWsLvlLo);
+  uint32_t* lvl_hi = reinterpret_cast<uint32_t*>(scratch + kWsLvlHi);
+  uint32_t* oprec = reinterpret_cast<uint32_t*>(scratch + kWsOprec);
+  uint32_t* endcnt = reinterpret_cast<uint32_t*>(scratch + kWsEndcnt);
+  uint16_t* leafrec = reinterpret_cast<uint16_t*>(scratch + kWsLeafrec);
+  lvl_lo[lane] = 0u; lvl_hi[lane] = 0u;
+  if (lane < 2) { lvl_lo[32 + lane] = 0u; lvl_hi[32 + lane] = 0u; }
+  endcnt[lane] = 0u; endcnt[lane + 32] = 0u;
+  __syncwarp();
+  // level masks: positions with the same S (index S + 1 in 0 .. 32)
+  const unsigned m0 = __match_any_sync(full, v0 ? s0 + 1 : 64 + lane);
+  const unsigned m1 = __match_any_sync(full, v1 ? s1 + 1 : 64 + lane);
+  if (v0 && __ffs(m0) - 1 == lane) lvl_lo[s0 + 1] = m0;
+  if (v1 && __ffs(m1) - 1 == lane) lvl_hi[s1 + 1] = m1;
+  __syncwarp();
+  auto level = [&](int sv) { return (unsigned long long)lvl_lo[sv + 1] | ((unsigned long long)lvl_hi[sv + 1] << 32); };
+  const unsigned long long validmask = mask_below(n);
+  // per position: end of the own subtree, right child (operators), parent, "changing" flag
+  int par[2], eself[2];
+  bool chg[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int p = h ? p1 : p0, sv = h ? s1 : s0;
+    const bool valid = h ? v1 : v0, isop = h ? op1 : op0;
+    const uint32_t tk = h ? tk1 : tk0;
+    par[h] = -1; eself[h] = p; chg[h] = false;
+    if (valid) {
+      const unsigned long long after = ~mask_below(p + 1);
+      if (p > 0) {
+        if ((opmask >> (p - 1)) & 1ULL) par[h] = p - 1;
+        else {
+          const int sprev = isop ? sv - 1 : sv + 1;
+          par[h] = 63 - __clzll((long long)(level(sprev + 1) & opmask & mask_below(p)));
+        }
+      }
+      if (isop) {
+        const int eol = __ffsll((long long)(level(sv - 1) & after)) - 1;   // end of the left subtree
+        eself[h] = __ffsll((long long)(level(sv - 2) & after)) - 1;
+        const bool mul = (mulmask >> p) & 1ULL;
+        chg[h] = p == 0 || (((mulmask >> par[h]) & 1ULL) != (mul ? 1ULL : 0ULL));
+        oprec[__popcll(opmask & mask_below(p))] = (uint32_t)p | ((uint32_t)(eol + 1) << 8) | ((mul ? 2u : 1u) << 16);
+      } else {
+        idpos[p] = leaf_class(tk);
+      }
+    }
+  }
+  const unsigned long long chgmask = (unsigned long long)__ballot_sync(full, chg[0]) | ((unsigned long long)__ballot_sync(full, chg[1]) << 32);
+  if (chg[0]) atomicAdd(&endcnt[eself[0]], 1u);
+  if (chg[1]) atomicAdd(&endcnt[eself[1]], 1u);
+  __syncwarp();
+  {  // inclusive prefix sums of endcnt over the 64 positions
+    uint32_t a = endcnt[lane], b = endcnt[lane + 32];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t xa = __shfl_up_sync(full, a, o), xb = __shfl_up_sync(full, b, o);
+      if (lane >= o) { a += xa; b += xb; }
+    }
+    b += __shfl_sync(full, a, 31);
+    __syncwarp();
+    endcnt[lane] = a; endcnt[lane + 32] = b;
+  }
+  __syncwarp();
+  const unsigned long long leafmask = ~opmask & validmask;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int p = h ? p1 : p0;
+    const bool valid = h ? v1 : v0, isop = h ? op1 : op0;
+    if (valid && !isop) {
+      const int runs = __popcll(chgmask & mask_below(p)) - (p ? (int)endcnt[p - 1] : 0);
+      const uint32_t code = runs ? 1u + 2u * (uint32_t)(runs - 1) + (uint32_t)((mulmask >> par[h]) & 1ULL) : 0u;
+      leafrec[__popcll(leafmask & mask_below(p))] = (uint16_t)((h ? tk1 : tk0) | (code << 8));
+    }
+  }
+  __syncwarp();
+  // class ids bottom-up: operator number `lane` fires when both children are ready
+  const int n_int = __popcll(opmask), n_leaf = n - n_int;
+  const bool mine = lane < n_int;
+  const uint32_t rec = mine ? oprec[lane] : 0u;
+  const int pos = rec & 0xff, right = (rec >> 8) & 0xff;
+  unsigned long long ready = leafmask, my_id = 0ULL;
+  bool done = !mine;
+  while (true) {
+    const bool go = !done && ((ready >> (pos + 1)) & 1ULL) && ((ready >> right) & 1ULL);
+    if (go) {
+      my_id = class_combine(rec >> 16, idpos[pos + 1], idpos[right]);
+      idpos[pos] = my_id;
+      done = true;
+    }
+    const uint32_t lo = __reduce_or_sync(full, (go && pos < 32) ? (1u << pos) : 0u);
+    const uint32_t hi = __reduce_or_sync(full, (go && pos >= 32) ? (1u << (pos - 32)) : 0u);
+    if ((lo | hi) == 0u) break;
+    ready |= (unsigned long long)lo | ((unsigned long long)hi << 32);
+    __syncwarp();
+  }
+  const uint32_t lr = leafrec[lane];
+  out.id = my_id;
+  out.meta = (uint32_t)n | ((uint32_t)n_leaf << 8) | ((uint32_t)n_int << 16);
+  out.sym = lr & 0xffu;
+  out.code = lr >> 8;
+  __syncwarp();
+  return out;
+}
+
+// zeroes the work counter (and the count of malformed records) of a fused-scan pair launch: what scan_kernel does on
+// the two-launch path
+__global__ void pair_init_kernel(unsigned long long* next, int32_t* bad_zero) {
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    *next = 0ULL;
+    if (bad_zero) *bad_zero = 0;
+  }
+}
+
 // ---- launch 2: warp-per-tree pairs ----------------------------------------------------------
 // exp_nonpos (fast_math.cuh) on G arguments at once: the same operations in the same order (bit-identical
 // results), but every coefficient is fetched once per group and the G Horner chains interleave.
@@ -243,7 +431,9 @@ __device__ __forceinline__ double u32_to_f64(uint32_t m) {
   return __hiloint2double(0x43300000, (int)m) - 4503599627370496.0;
 }
 
-template <int R, bool kExtra>  // R: evaluated trees per lane per tile; kExtra: also write D and/or Df
+// R: evaluated trees per lane per tile; kExtra: also write D and/or Df; kFused: no scan launch in front, every warp scans
+// its candidate itself (warp_scan_tree) straight from the flat records
+template <int R, bool kExtra, bool kFused>
 __global__ void __launch_bounds__(kMaxPairWarps * 32, 1)
 sot_pair_kernel(PairParams p, bosot_grammar g) {
   constexpr int RP = (R + 1) / 2;  // packed pairs of evaluated trees per lane
@@ -294,7 +484,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   const uint8_t* e_nn = smem + S.off_nn;
   const uint8_t* e_nl = smem + S.off_nl;
 
-  const WarpLayout W = warp_layout(e_pad, g.n_dim_cols, g.n_blocks);
+  const WarpLayout W = warp_layout(e_pad, g.n_dim_cols, g.n_blocks, kFused);
   uint8_t* wbase = smem + S.total + (size_t)warp * W.total;
   double* avec = reinterpret_cast<double*>(wbase);                   // candidate DIM_WISE vector, permuted column order
   double* tab = reinterpret_cast<double*>(wbase + W.off_tab);        // tab[b][s] = L1(candidate block b, state s)
@@ -310,8 +500,9 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   const size_t plane = (size_t)p.n_cand * p.ld;
   const int ld_i = p.ld < (int64_t)e_pad ? (int)p.ld : e_pad;  // columns this kernel may touch
 
+  uint8_t* wscan = wbase + W.off_scan;                               // fused-scan path: scratch of warp_scan_tree
+
   // one lane-slice of a compact record: class id of operator node `lane`, symbol / path code of leaf `lane`
-  struct Slice { unsigned long long id; uint32_t meta, sym, code; };
   auto load_slice = [&](int64_t t) {
     Slice s;
     const uint8_t* r = p.recs + (size_t)t * kScanBytes;
@@ -324,28 +515,43 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
 
   // Work distribution.  Trees differ in cost by an order of magnitude (1 .. 63 nodes), and with a static stride the warp
   // with the unluckiest share decided when the kernel ended, so candidates are claimed one at a time from a global
-  // counter -- but never waited for: every warp starts on two candidates it owns by position (its index in the grid
-  // and that plus the number of warps: no atomic on the way to the first tree, which at small pools was a stampede of
-  // thousands of warps on one address, 30 % of all stall samples at 10k candidates), and the claim issued at the top of
-  // iteration i is only read at its end, as the index of candidate i + 2 (its record is prefetched during iteration
-  // i + 1).  The counter hands out the positions from 2 W on.
+  // counter, one claim ahead of the work.  The FIRST candidate of every warp is its own index in the grid -- no atomic
+  // on the way to the first tree: at small pools the first claims were a stampede of thousands of warps on one address
+  // (30 % of all stall samples at 10k candidates, profiles/r2f) -- and the counter hands out the positions from W on.
+  // (Claiming two ahead, so that the atomic is never waited for, measured slower: 42.0 against 37.9 us at 10k x 50,
+  // no difference at 1M x 200, profiles/r2h_ab.log.)
   const int64_t n_warps_grid = (int64_t)gridDim.x * n_warps;
   pdl_wait();  // the scan launch has completed: work counter zeroed, compact records visible
   int64_t t = (int64_t)blockIdx.x + (int64_t)gridDim.x * warp;  // neighbouring warps of a CTA take trees far apart
-  int64_t t1 = t + n_warps_grid;
   Slice nxt;
-  if (t < p.n_cand) nxt = load_slice(t);
+  RawTree nraw;
+  if (t < p.n_cand) {
+    if (kFused) nraw = load_raw(p.trees + (size_t)t * kTreeBytes, lane);
+    else nxt = load_slice(t);
+  }
   mbar_wait(bar, 0);  // tables landed (the copy overlapped the first record load)
   const bool use_states = meta->use_states != 0;
   const int n_flat = meta->n_flat;
 
 #pragma unroll 1
   for (int e = 2 * lane; e < e_pad; e += 64) *reinterpret_cast<uint2*>(acc + e) = make_uint2(0u, 0u);
-  unsigned long long pending = 0ULL;
-  for (; t < p.n_cand; t = t1, t1 = 2 * n_warps_grid + (int64_t)__shfl_sync(full, pending, 0)) {
-    const Slice cur = nxt;
-    if (lane == 0) pending = atomicAdd(p.next, 1ULL);  // candidate after next; consumed by the loop increment
-    if (t1 < p.n_cand) nxt = load_slice(t1);           // prefetch the next record behind this tree's work
+  auto claim = [&]() {
+    unsigned long long v = 0ULL;
+    if (lane == 0) v = atomicAdd(p.next, 1ULL);
+    return n_warps_grid + (int64_t)__shfl_sync(full, v, 0);
+  };
+  for (int64_t t1; t < p.n_cand; t = t1) {
+    Slice cur;
+    t1 = claim();
+    if (kFused) {
+      const RawTree craw = nraw;
+      if (t1 < p.n_cand) nraw = load_raw(p.trees + (size_t)t1 * kTreeBytes, lane);  // prefetch behind this tree's work
+      cur = warp_scan_tree(craw, p.trees + (size_t)t * kTreeBytes, p.n_symbols, wscan, lane);
+      if (p.status && lane == 0) p.status[t] = (int32_t)(cur.meta >> 24);
+    } else {
+      cur = nxt;
+      if (t1 < p.n_cand) nxt = load_slice(t1);  // prefetch the next record behind this tree's work
+    }
 
     const int nn = cur.meta & 0xff, nl = (cur.meta >> 8) & 0xff, ni = (cur.meta >> 16) & 0xff;
     const bool bad = (cur.meta >> 24) != 0;
@@ -616,30 +822,41 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   p.ld = ld;
   p.next = static_cast<unsigned long long*>(d_scratch);
   p.bad = d_bad;
+  p.flags = experiment_flag();
+  p.status = d_status;
+  p.n_symbols = grammar->n_symbols;
   p.recs = static_cast<const uint8_t*>(d_scratch) + kScratchHead;
 
   int dev = 0, sms = 0;
   if (int rc = cuda_check(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
   if (int rc = cuda_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return rc;
 
-  // launch 1: scan
-  static std::atomic<bool> scan_attr[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
-  if (!(dev < 64 && scan_attr[dev])) {
-    if (int rc = cuda_check(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanThreads * kRecBytes),
-                            "cudaFuncSetAttribute(scan_kernel)")) return rc;
-    if (dev < 64) scan_attr[dev] = true;
+  // Small pools (and the evaluated set itself): no scan launch, every warp scans its own candidates
+  // (warp_scan_tree); beyond kFusedScanMax candidates the thread-per-tree scan launch is cheaper in issue slots.
+  const bool fused = n_cand <= kFusedScanMax && !(experiment_flag() & 2);
+  if (fused) {
+    pair_init_kernel<<<1, 32, 0, stream>>>(p.next, zero_bad ? d_bad : nullptr);
+    if (int rc = after_launch("pair_init_kernel")) return rc;
+  } else {
+    // launch 1: scan
+    static std::atomic<bool> scan_attr[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
+    if (!(dev < 64 && scan_attr[dev])) {
+      if (int rc = cuda_check(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanThreads * kRecBytes),
+                              "cudaFuncSetAttribute(scan_kernel)")) return rc;
+      if (dev < 64) scan_attr[dev] = true;
+    }
+    const int64_t scan_blocks = (n_cand + kScanThreads - 1) / kScanThreads;
+    if (scan_blocks > 0x7fffffffLL) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: too many candidates");
+    scan_kernel<<<(unsigned)scan_blocks, kScanThreads, kScanThreads * kRecBytes, stream>>>(
+        d_trees, n_cand, grammar->n_symbols, static_cast<uint8_t*>(d_scratch) + kScratchHead, d_status, p.next, zero_bad ? d_bad : nullptr);
+    if (int rc = after_launch("scan_kernel")) return rc;
   }
-  const int64_t scan_blocks = (n_cand + kScanThreads - 1) / kScanThreads;
-  if (scan_blocks > 0x7fffffffLL) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: too many candidates");
-  scan_kernel<<<(unsigned)scan_blocks, kScanThreads, kScanThreads * kRecBytes, stream>>>(
-      d_trees, n_cand, grammar->n_symbols, static_cast<uint8_t*>(d_scratch) + kScratchHead, d_status, p.next, zero_bad ? d_bad : nullptr);
-  if (int rc = after_launch("scan_kernel")) return rc;
 
   // launch 2: pairs.  One persistent CTA per SM; small pools shrink the CTA so that every SM gets warps.
   int warps = kMaxPairWarps;
   while (warps > 1 && (n_cand + warps - 1) / warps < sms) warps >>= 1;
   const StageLayout S = stage_layout(p.L.e_pad, grammar->n_dim_cols, grammar->n_symbols, grammar->n_blocks);
-  const size_t per_warp = warp_layout(p.L.e_pad, grammar->n_dim_cols, grammar->n_blocks).total;
+  const size_t per_warp = warp_layout(p.L.e_pad, grammar->n_dim_cols, grammar->n_blocks, fused).total;
   const size_t smem_cap = 220 * 1024;
   size_t smem = S.total + (size_t)warps * per_warp;
   while (smem > smem_cap && warps > 1) {
@@ -652,17 +869,16 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   const int rounds = (n_eval + 31) / 32;  // evaluated trees per lane; beyond 256 trees: tiles of 256 (e_pad is a multiple of 256)
   const int R = rounds < kMaxR ? rounds : kMaxR;
   using KernelFn = void (*)(PairParams, bosot_grammar);
-  static const KernelFn table[kMaxR][2] = {
-      {sot_pair_kernel<1, false>, sot_pair_kernel<1, true>}, {sot_pair_kernel<2, false>, sot_pair_kernel<2, true>},
-      {sot_pair_kernel<3, false>, sot_pair_kernel<3, true>}, {sot_pair_kernel<4, false>, sot_pair_kernel<4, true>},
-      {sot_pair_kernel<5, false>, sot_pair_kernel<5, true>}, {sot_pair_kernel<6, false>, sot_pair_kernel<6, true>},
-      {sot_pair_kernel<7, false>, sot_pair_kernel<7, true>}, {sot_pair_kernel<8, false>, sot_pair_kernel<8, true>}};
-  KernelFn kernel = table[R - 1][extra ? 1 : 0];
+#define BOSOT_PAIR_ROW(r) {{sot_pair_kernel<r, false, false>, sot_pair_kernel<r, false, true>}, {sot_pair_kernel<r, true, false>, sot_pair_kernel<r, true, true>}}
+  static const KernelFn table[kMaxR][2][2] = {BOSOT_PAIR_ROW(1), BOSOT_PAIR_ROW(2), BOSOT_PAIR_ROW(3), BOSOT_PAIR_ROW(4),
+                                              BOSOT_PAIR_ROW(5), BOSOT_PAIR_ROW(6), BOSOT_PAIR_ROW(7), BOSOT_PAIR_ROW(8)};
+#undef BOSOT_PAIR_ROW
+  KernelFn kernel = table[R - 1][extra ? 1 : 0][fused ? 1 : 0];
   static std::atomic<bool> attr_set[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
   if (!(dev < 64 && attr_set[dev])) {
     for (int r = 0; r < kMaxR; ++r)
-      for (int x = 0; x < 2; ++x)
-        if (int rc = cuda_check(cudaFuncSetAttribute(table[r][x], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
+      for (int x = 0; x < 4; ++x)
+        if (int rc = cuda_check(cudaFuncSetAttribute(table[r][x >> 1][x & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
                                 "cudaFuncSetAttribute(sot_pair_kernel)")) return rc;
     if (dev < 64) attr_set[dev] = true;
   }
@@ -674,7 +890,9 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   const int64_t want = (n_cand + warps - 1) / warps;
   const int64_t wave = (int64_t)sms * per_sm;
   const int64_t grid = want < wave ? want : wave;
-  if (int rc = cuda_check(launch_pdl(kernel, dim3((unsigned)grid), dim3(warps * 32), smem, stream, p, *grammar), "cudaLaunchKernelEx(sot_pair_kernel)")) return rc;
+  // programmatic dependent launch pays where launch latency matters (10k x 50: 54 against 58 us per step) and costs
+  // 4 % at 1M x 200 (profiles/r2h_ab.log), so only the small-pool path chains its launches that way
+  if (int rc = cuda_check(launch_pdl(fused, kernel, dim3((unsigned)grid), dim3(warps * 32), smem, stream, p, *grammar), "cudaLaunchKernelEx(sot_pair_kernel)")) return rc;
   return after_launch("sot_pair_kernel");
 }
 
