@@ -41,7 +41,8 @@ int experiment_flag();
 constexpr int kMaxPairWarps = 28;   // one persistent CTA of up to 28 warps per SM (72 registers per thread; measured: 20 / 24 / 28 / 32 warps = 2.68 / 2.52 / 2.43 / 2.49 ms)
 constexpr int kScanThreads = 128;
 constexpr int kMaxR = 8;            // evaluated trees per lane per register tile (E <= 256 in one pass, else tiles of 256)
-constexpr int64_t kFusedScanMax = 32768;  // pools up to this size take the fused-scan path (no scan launch)
+constexpr int64_t kFusedScanMax = 16384;  // pools up to this size take the fused-scan path (no scan launch); measured
+                                          // 10k x 50: 48 against 56 us per step, 100 x 50: 21 against 34 us, 30k x 80: 110 against 101 us (profiles/r2i_ab.log)
 
 // Small tables, initialised STATICALLY (constant-folded by the host compiler, so correctly rounded like Python's
 // float(a) / float(b)): nothing is uploaded at run time, hence nothing to order against the caller's stream.

@@ -198,3 +198,58 @@ def test_shutdown_releases_the_host_pipeline_and_the_library_stays_usable():
     assert _lib.load().bosot_shutdown() == 0  # idempotent
     eng.acquire_host(h_trees, b)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n_eval", [50, 200])
+def test_fused_scan_and_scan_launch_paths_agree_bit_for_bit(n_eval):
+    """Pools of up to 16384 candidates are scanned inside the pair kernel (warp-cooperative closed-form scan), larger
+    ones by the thread-per-tree scan launch: the same candidates through both routes -- alone, and as the head of a
+    pool large enough for the scan launch -- must give the same bits, defect codes of malformed records included."""
+    gram, ev_np, y, hyp, eng = _engine(n_eval)
+    big = random_stress_trees(40_000, gram, seed=21)
+    names = gram.symbols
+    from bosot_b200.encoding import encode
+
+    chains = [names[0]]
+    for k in range(2, 33):  # left- and right-deep chains up to 63 nodes: the deepest level structure the scan can meet
+        t = names[k % len(names)]
+        for i in range(1, k):
+            t = ("ADD" if (i * k) % 3 else "MULTIPLY", t, names[i % len(names)]) if k % 2 else ("MULTIPLY" if i % 2 else "ADD", names[i % len(names)], t)
+        chains.append(t)
+    big[100:100 + len(chains)] = encode(chains, gram)
+    big[7, 0] = 4                      # even length
+    big[8, 0] = 0                      # zero length
+    big[9, :4] = [3, 0x85, 1, 2]       # unknown operator
+    big[10, :4] = [3, 0x80, 70, 1]     # symbol out of range
+    big[11, 0] = 65                    # too long
+    big[12, :4] = [3, 0x80, 0x80, 1]  # too few operands
+    big[13, :4] = [3, 1, 2, 3]        # too many operands
+    small = big[:6000]
+    w = hyp.alphas / hyp.alphas.sum()
+    a = sot.sot_pairs(sot.as_device_trees(small, DEV), eng.state, w, hyp.variance, hyp.lengthscale, want=("K", "D", "Df"), check=False)
+    b = sot.sot_pairs(sot.as_device_trees(big, DEV), eng.state, w, hyp.variance, hyp.lengthscale, want=("K", "D", "Df"), check=False)
+    for key in ("K", "D", "Df"):
+        x, z = a[key], b[key][..., :6000, :] if key == "Df" else b[key][:6000]
+        assert torch.equal(torch.isnan(x), torch.isnan(z)), key
+        assert torch.equal(torch.nan_to_num(x), torch.nan_to_num(z)), key
+    assert bool(torch.isnan(a["K"][7:14]).all()) and not bool(torch.isnan(a["K"][14:]).any())
+    lib = _lib.load()
+    import ctypes as C
+
+    def status_of(trees_np):
+        t = sot.as_device_trees(trees_np, DEV)
+        n = t.shape[0]
+        st = torch.empty(n, dtype=torch.int32, device=DEV)
+        K = torch.empty((n, n_eval), dtype=torch.float64, device=DEV)
+        scratch = torch.empty(lib.bosot_sot_pairs_scratch_bytes(n), dtype=torch.uint8, device=DEV)
+        _lib.check(lib.bosot_sot_pairs(t.data_ptr(), n, C.byref(gram.c_struct), eng.state.blob.data_ptr(), n_eval, (C.c_double * 3)(*w), 1.0, 1.0,
+                                       K.data_ptr(), None, None, n_eval, st.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                       torch.cuda.current_stream().cuda_stream))
+        return st.cpu().numpy()
+
+    s_small, s_big = status_of(small), status_of(big)
+    assert np.array_equal(s_small, s_big[:6000])
+    assert list(np.nonzero(s_small)[0]) == [7, 8, 9, 10, 11, 12, 13]
+    mu_s, sg_s, ei_s = eng.acquire_device(sot.as_device_trees(small[14:], DEV))
+    mu_b, sg_b, ei_b = eng.acquire_device(sot.as_device_trees(big[14:], DEV))
+    assert torch.equal(mu_s, mu_b[:5986]) and torch.equal(sg_s, sg_b[:5986]) and torch.equal(ei_s, ei_b[:5986])
