@@ -590,7 +590,7 @@ __device__ __forceinline__ void pair_body(const PairParams& p, const bosot_gramm
                                              : (p.K ? p.K + row : nullptr);
     auto ring_wait_free = [&]() {  // the posterior warps have released every earlier use of the slot
       if (kMode == kPairTiles) {
-        while (*((volatile int*)&ring.ctl[kRingReleased + ring_slot]) < ring_use) __nanosleep(64);
+        while (*((volatile int*)&ring.ctl[kRingReleased + ring_slot]) < ring_use) __nanosleep(1000);
         __threadfence_block();
       }
     };
@@ -1060,7 +1060,7 @@ sot_fused_kernel(PairParams pp, bosot_grammar g, PostParams qp) {
     pair_body<R, false, kPairTiles>(pp, g, smem, bar, warp, kFusedPairWarps, ring);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
-    posterior_consume<kFusedTC, 2>(qp, ring, reinterpret_cast<double*>(smem + F.off_red), reinterpret_cast<double*>(smem + F.off_mus));
+    posterior_consume<kFusedTC, 8>(qp, ring, reinterpret_cast<double*>(smem + F.off_red), reinterpret_cast<double*>(smem + F.off_mus));
   }
 }
 

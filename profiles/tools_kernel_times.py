@@ -19,7 +19,13 @@ gram = Grammar.get("CKSHighDimSearchSpace", 5)
 alphas = np.array([0.2, 0.7, 0.4])
 w = alphas / alphas.sum()
 ev = sot.as_device_trees(random_stress_trees(n_eval, gram, seed=77), dev)
-ca = sot.as_device_trees(random_stress_trees(pool, gram, seed=1234), dev)
+import os
+_ca_np = random_stress_trees(pool, gram, seed=1234)
+if os.environ.get("BOSOT_UNIFORM"):  # experiment: every candidate the same size (no stragglers inside a tile)
+    _n = int(os.environ["BOSOT_UNIFORM"])
+    _sel = _ca_np[_ca_np[:, 0] == _n]
+    _ca_np = _sel[np.arange(pool) % len(_sel)].copy()
+ca = sot.as_device_trees(_ca_np, dev)
 y = np.random.default_rng(4).standard_normal(n_eval)
 eng = sot.AcquisitionEngine(ev, torch.from_numpy(y), gram, w, 1.3, 0.8, 1e-3, -0.5)
 K = torch.empty((pool, n_eval), dtype=torch.float64, device=dev)
