@@ -57,12 +57,6 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
                  double* d_Df, int64_t ld, int32_t* d_status, void* d_scratch, size_t scratch_bytes, cudaStream_t stream,
                  int32_t* d_bad, bool zero_bad);
 size_t pairs_scratch_bytes(int64_t n_cand);
-int launch_acquire_fused(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar, const void* d_eval_blob, int n_eval,
-                         const double weights[3], double variance, double lengthscale, const double* d_Linv, int ldl,
-                         const double* d_beta, double mean_c, int acq_kind, const double* d_current_max, double xi, double ucb_beta,
-                         int32_t* d_status, void* d_scratch, size_t scratch_bytes, double* d_mu, double* d_sigma, double* d_acq,
-                         int32_t* d_bad, bool zero_bad, double* const* d_peers, int n_peers, int64_t peer_off, cudaStream_t stream,
-                         bool* used);
 int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval, const double* d_Linv, int ldl,
                      const double* d_beta, double mean_c, double variance, int acq_kind, const double* d_current_max,
                      double xi, double ucb_beta, double* d_mu, double* d_sigma, double* d_acq, cudaStream_t stream,
@@ -220,12 +214,6 @@ static int acquire_on_device(const char* who, const uint8_t* d_trees, int64_t n_
   double* K = reinterpret_cast<double*>(w + W.off_K);
   int32_t* status = reinterpret_cast<int32_t*>(w + W.off_status);
   if (n_cand == 0 && d_n_bad) return cuda_check(cudaMemsetAsync(d_n_bad, 0, sizeof(int32_t), st), "cudaMemsetAsync");
-  // large pools: pairs and posterior in one kernel, K* stays in shared memory
-  bool fused = false;
-  if (int rc = launch_acquire_fused(d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale, d_Linv, ldl, d_beta,
-                                    mean_c, acq_kind, d_current_max, xi, ucb_beta, status, w + W.off_recs, pairs_scratch_bytes(n_cand),
-                                    d_mu, d_sigma, d_acq, d_n_bad, true, d_peers, n_peers, peer_off, st, &fused)) return rc;
-  if (fused) return BOSOT_OK;
   // one set of launches: cutting a device-resident pool into chunks on two streams was measured slower (4.07 vs 3.95 ms)
   if (int rc = launch_pairs(d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale, K, nullptr,
                             nullptr, W.ld, status, w + W.off_recs, pairs_scratch_bytes(n_cand), st, d_n_bad, true)) return rc;
@@ -355,17 +343,9 @@ static int acquire_from_host(const char* who, const uint8_t* h_trees, int64_t n_
       if (int rc = cuda_check(cudaEventRecord(P.copied[k], P.h2d), "cudaEventRecord")) return rc;
       cudaStream_t cs = (k & 1) ? P.alt : st;
       if (int rc = cuda_check(cudaStreamWaitEvent(cs, P.copied[k], 0), "cudaStreamWaitEvent")) return rc;
-      bool fused = false;
-      if (int rc = launch_acquire_fused(d_trees + c0 * kTreeBytes, n, grammar, d_eval_blob, n_eval, weights, variance, lengthscale, d_Linv, ldl,
-                                        d_beta, mean_c, acq_kind, d_current_max, xi, ucb_beta, d_status + c0,
-                                        d_recs + (size_t)c0 * kScanBytes + 16 * (size_t)k, pairs_scratch_bytes(n),
-                                        h_mu ? d_mu + c0 : nullptr, h_sigma ? d_sigma + c0 : nullptr, want_acq ? d_acq + c0 : nullptr,
-                                        d_bad, false, d_peers, n_peers, peer_off + c0, cs, &fused)) return rc;
-      if (!fused)
       if (int rc = launch_pairs(d_trees + c0 * kTreeBytes, n, grammar, d_eval_blob, n_eval, weights, variance, lengthscale,
                                 d_K + c0 * W.ld, nullptr, nullptr, W.ld, d_status + c0, d_recs + (size_t)c0 * kScanBytes + 16 * (size_t)k,
                                 pairs_scratch_bytes(n), cs, d_bad, false)) return rc;  // chunk k: its own scratch head, then its records
-      if (!fused)
       if (int rc = launch_posterior(d_K + c0 * W.ld, n, W.ld, n_eval, d_Linv, ldl, d_beta, mean_c, variance, acq_kind, d_current_max,
                                     xi, ucb_beta, h_mu ? d_mu + c0 : nullptr, h_sigma ? d_sigma + c0 : nullptr,
                                     want_acq ? d_acq + c0 : nullptr, cs, d_peers, n_peers, peer_off + c0)) return rc;

@@ -33,7 +33,6 @@
 #include "sot_common.cuh"
 #include "launch.cuh"
 #include "fast_math.cuh"
-#include "posterior_common.cuh"
 
 namespace bosot {
 
@@ -433,22 +432,30 @@ __device__ __forceinline__ double u32_to_f64(uint32_t m) {
   return __hiloint2double(0x43300000, (int)m) - 4503599627370496.0;
 }
 
-// Shared-memory ring between the pair warps (producers of K* rows) and the posterior warps of sot_fused_kernel.
-// ctl: [0] rows handed out, [1..2] rows written per slot (cumulative), [3..4] tiles released per slot (cumulative),
-//      [5] posterior work counter, [6..7] units done per slot
-struct TileRing {
-  int* ctl;
-  double* tiles;   // [2][tc][tld]
-  int tld, tc;
-};
-constexpr int kRingRows = 0, kRingFilled = 1, kRingReleased = 3, kRingWork = 5, kRingDone = 6;
-enum { kPairGlobal = 0, kPairFusedScan = 1, kPairTiles = 2 };
+// R: evaluated trees per lane per tile; kExtra: also write D and/or Df; kFused: no scan launch in front, every warp scans
+// its candidate itself (warp_scan_tree) straight from the flat records
+template <int R, bool kExtra, bool kFused>
+__global__ void __launch_bounds__(kMaxPairWarps * 32, 1)
+sot_pair_kernel(PairParams p, bosot_grammar g) {
+  constexpr int RP = (R + 1) / 2;  // packed pairs of evaluated trees per lane
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int n_warps = blockDim.x >> 5;
+  const int E = p.L.n_eval;
+  const int e_pad = p.L.e_pad;
+  const int half_pad = e_pad >> 1;
+  const unsigned full = 0xffffffffu;
+  const unsigned lt_mask = (1u << lane) - 1u, le_mask = (2u << lane) - 1u;
 
-// stage the evaluated set's dense tables once per (persistent) CTA: TMA bulk copies -> mbarrier (ONE thread calls this
-// after the barrier has been initialised and made visible)
-__device__ __forceinline__ void pair_stage_tables(const PairParams& p, const bosot_grammar& g, uint8_t* smem, uint64_t* bar) {
-  const StageLayout S = stage_layout(p.L.e_pad, g.n_dim_cols, g.n_symbols, g.n_blocks);
-  {
+  pdl_launch_dependents();  // a posterior launch behind this one may set up its shared memory early (it waits before reading K*)
+  // ---- stage the evaluated set's dense tables once per (persistent) CTA: TMA bulk copies -> mbarrier
+  // (the blob is the product of an OLDER launch than the scan in front of this one, so this may run before pdl_wait())
+  const StageLayout S = stage_layout(e_pad, g.n_dim_cols, g.n_symbols, g.n_blocks);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
     const int states = __ldg(reinterpret_cast<const int*>(p.blob + p.L.off_meta));  // DimMeta::use_states
     mbar_expect_tx(bar, S.b_meta + (states ? S.b_state + S.b_sid + S.b_flat : S.b_dimT) + 2 * S.b_r + S.b_symT2 + S.b_nn2 + 2 * S.b_n);
     tma_bulk_g2s(smem + S.off_meta, p.blob + p.L.off_meta, S.b_meta, bar);
@@ -466,24 +473,6 @@ __device__ __forceinline__ void pair_stage_tables(const PairParams& p, const bos
     tma_bulk_g2s(smem + S.off_nn, p.blob + p.L.off_nnodes, S.b_n, bar);
     tma_bulk_g2s(smem + S.off_nl, p.blob + p.L.off_nleaves, S.b_n, bar);
   }
-}
-
-// The pair work of one warp.  R: evaluated trees per lane per tile; kExtra: also write D and/or Df; kMode:
-//   kPairGlobal     rows of K* to global memory, compact records from the scan launch in front;
-//   kPairFusedScan  rows to global memory, every warp scans its candidate itself (warp_scan_tree): no scan launch;
-//   kPairTiles      rows into the shared-memory tile ring of sot_fused_kernel (compact records from the scan launch).
-template <int R, bool kExtra, int kMode>
-__device__ __forceinline__ void pair_body(const PairParams& p, const bosot_grammar& g, uint8_t* smem, uint64_t* bar, const int warp,
-                                          const int n_warps, const TileRing ring) {
-  constexpr int RP = (R + 1) / 2;  // packed pairs of evaluated trees per lane
-  constexpr bool kFused = kMode == kPairFusedScan;
-  const int lane = threadIdx.x & 31;
-  const int E = p.L.n_eval;
-  const int e_pad = p.L.e_pad;
-  const int half_pad = e_pad >> 1;
-  const unsigned full = 0xffffffffu;
-  const unsigned lt_mask = (1u << lane) - 1u, le_mask = (2u << lane) - 1u;
-  const StageLayout S = stage_layout(e_pad, g.n_dim_cols, g.n_symbols, g.n_blocks);
   const DimMeta* meta = reinterpret_cast<const DimMeta*>(smem + S.off_meta);
   const double* stateP = reinterpret_cast<const double*>(smem + S.off_dim);  // [n_pcols][kMaxStates]   (state mode)
   const double* dimT = stateP;                                               // [n_pcols][e_pad]        (dense mode)
@@ -510,7 +499,7 @@ __device__ __forceinline__ void pair_body(const PairParams& p, const bosot_gramm
   const uint32_t* post = reinterpret_cast<const uint32_t*>(p.blob + p.L.off_post);
   const int hash_cap = p.L.hash_cap;
   const size_t plane = (size_t)p.n_cand * p.ld;
-  const int ld_i = kMode == kPairTiles ? ring.tld : (p.ld < (int64_t)e_pad ? (int)p.ld : e_pad);  // columns this kernel may touch
+  const int ld_i = p.ld < (int64_t)e_pad ? (int)p.ld : e_pad;  // columns this kernel may touch
 
   uint8_t* wscan = wbase + W.off_scan;                               // fused-scan path: scratch of warp_scan_tree
 
@@ -532,24 +521,9 @@ __device__ __forceinline__ void pair_body(const PairParams& p, const bosot_gramm
   // (30 % of all stall samples at 10k candidates, profiles/r2f) -- and the counter hands out the positions from W on.
   // (Claiming two ahead, so that the atomic is never waited for, measured slower: 42.0 against 37.9 us at 10k x 50,
   // no difference at 1M x 200, profiles/r2h_ab.log.)
-  // kPairTiles: the CTA owns the tiles blockIdx.x, blockIdx.x + gridDim.x, ... of ring.tc consecutive candidates (a tile
-  // of 32 random trees averages the cost spread out, and a CTA works through ~200 of them), its warps take the rows of
-  // those tiles one by one from a shared-memory counter: row g = tile g / tc of this CTA, row g % tc; the first position
-  // at or beyond n_cand ends the warp (every later one lies beyond it too).
   const int64_t n_warps_grid = (int64_t)gridDim.x * n_warps;
-  int g_cur = 0, g_nxt = 0;  // kPairTiles: ring positions of the current / next candidate
-  auto ring_candidate = [&](int gpos) {
-    return ((int64_t)blockIdx.x + (int64_t)(gpos / ring.tc) * gridDim.x) * ring.tc + (gpos % ring.tc);
-  };
-  auto ring_claim = [&]() {
-    int v = 0;
-    if (lane == 0) v = atomicAdd(&ring.ctl[kRingRows], 1);
-    return __shfl_sync(full, v, 0);
-  };
   pdl_wait();  // the scan launch has completed: work counter zeroed, compact records visible
-  int64_t t;
-  if (kMode == kPairTiles) { g_cur = ring_claim(); t = ring_candidate(g_cur); }
-  else t = (int64_t)blockIdx.x + (int64_t)gridDim.x * warp;  // neighbouring warps of a CTA take trees far apart
+  int64_t t = (int64_t)blockIdx.x + (int64_t)gridDim.x * warp;  // neighbouring warps of a CTA take trees far apart
   Slice nxt;
   RawTree nraw;
   if (t < p.n_cand) {
@@ -563,12 +537,11 @@ __device__ __forceinline__ void pair_body(const PairParams& p, const bosot_gramm
 #pragma unroll 1
   for (int e = 2 * lane; e < e_pad; e += 64) *reinterpret_cast<uint2*>(acc + e) = make_uint2(0u, 0u);
   auto claim = [&]() {
-    if (kMode == kPairTiles) { g_nxt = ring_claim(); return ring_candidate(g_nxt); }
     unsigned long long v = 0ULL;
     if (lane == 0) v = atomicAdd(p.next, 1ULL);
     return n_warps_grid + (int64_t)__shfl_sync(full, v, 0);
   };
-  for (int64_t t1; t < p.n_cand; t = t1, g_cur = g_nxt) {
+  for (int64_t t1; t < p.n_cand; t = t1) {
     Slice cur;
     t1 = claim();
     if (kFused) {
@@ -584,38 +557,19 @@ __device__ __forceinline__ void pair_body(const PairParams& p, const bosot_gramm
     const int nn = cur.meta & 0xff, nl = (cur.meta >> 8) & 0xff, ni = (cur.meta >> 16) & 0xff;
     const bool bad = (cur.meta >> 24) != 0;
     const size_t row = (size_t)t * p.ld;
-    // where this candidate's Gram row goes: global memory, or its row of the tile ring (slot = tile parity)
-    const int ring_slot = (g_cur / ring.tc) & 1, ring_use = (g_cur / ring.tc) >> 1;
-    double* const Krow = kMode == kPairTiles ? ring.tiles + ((size_t)ring_slot * ring.tc + (g_cur % ring.tc)) * ring.tld
-                                             : (p.K ? p.K + row : nullptr);
-    auto ring_wait_free = [&]() {  // the posterior warps have released every earlier use of the slot
-      if (kMode == kPairTiles) {
-        while (*((volatile int*)&ring.ctl[kRingReleased + ring_slot]) < ring_use) __nanosleep(1000);
-        __threadfence_block();
-      }
-    };
-    auto ring_publish = [&]() {    // the row is complete
-      if (kMode == kPairTiles) {
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) atomicAdd(&ring.ctl[kRingFilled + ring_slot], 1);
-      }
-    };
 
     if (bad) {  // malformed record: poison the row, status already written by the scan (cold path: keep it small)
       const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-      ring_wait_free();
 #pragma unroll 1
       for (int e = lane; e < ld_i; e += 32) {  // padding columns stay finite like those of every other row
         const double v = e < E ? qnan : 0.0;
-        if (Krow) Krow[e] = v;
+        if (p.K) p.K[row + e] = v;
         if (e < E) {
           if (p.D) p.D[row + e] = v;
           if (p.Df) { p.Df[row + e] = v; p.Df[plane + row + e] = v; p.Df[2 * plane + row + e] = v; }
         }
       }
       if (lane == 0 && p.bad) atomicAdd(p.bad, 1);
-      ring_publish();
       continue;
     }
 
@@ -725,7 +679,6 @@ __device__ __forceinline__ void pair_body(const PairParams& p, const bosot_gramm
     }
     __syncwarp();
 
-    ring_wait_free();
     // ---- phase C: register tiles of R evaluated trees per lane (tree e = e0 + lane + 32 r)
     const double rTa2_sub = 2.0 * c_recip.v[nn], rTa2_path = 2.0 * c_recip.v[nl];
     for (int e0 = 0; e0 < E; e0 += 32 * R) {
@@ -816,7 +769,7 @@ __device__ __forceinline__ void pair_body(const PairParams& p, const bosot_gramm
             x[i] = 0.0;
           }
         }
-        if (Krow) {
+        if (p.K) {
           exp_nonpos_group<kG>(x);
 #pragma unroll
           for (int i = 0; i < kG; ++i)  // pin the results here: otherwise every chain is sunk into its own guarded store
@@ -826,322 +779,20 @@ __device__ __forceinline__ void pair_body(const PairParams& p, const bosot_gramm
             const int r = r0 + i, e = eb + 32 * r;
             if (r < R) {
               // R = ceil(E / 32) when there is one tile (R < kMaxR): every row but the last lies inside E
-              if (R < kMaxR && r < R - 1) Krow[e] = p.variance * x[i];
+              if (R < kMaxR && r < R - 1) p.K[row + e] = p.variance * x[i];
               // padding columns of the Gram row stay finite (the posterior kernel may read them)
-              else if (e < ld_i) Krow[e] = e < E ? p.variance * x[i] : 0.0;
+              else if (e < ld_i) p.K[row + e] = e < E ? p.variance * x[i] : 0.0;
             }
           }
         }
       }
     }
-    ring_publish();
-  }
-}
-
-template <int R, bool kExtra, bool kFused>
-__global__ void __launch_bounds__(kMaxPairWarps * 32, 1)
-sot_pair_kernel(PairParams p, bosot_grammar g) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  pdl_launch_dependents();  // a posterior launch behind this one may set up its shared memory early (it waits before reading K*)
-  // (the blob is the product of an OLDER launch than the scan in front of this one, so the staging may run before pdl_wait())
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-  if (threadIdx.x == 0) mbar_init(bar, 1);
-  __syncthreads();
-  if (threadIdx.x == 0) pair_stage_tables(p, g, smem, bar);
-  pair_body<R, kExtra, kFused ? kPairFusedScan : kPairGlobal>(p, g, smem, bar, threadIdx.x >> 5, blockDim.x >> 5, TileRing{nullptr, nullptr, 0, 1});
-}
-
-// ---- pairs + posterior in ONE kernel (large pools) ----------------------------------------------------------------
-// The pair work saturates the issue slots and leaves the fp64 pipe three quarters idle; the posterior saturates the
-// fp64 tensor pipe and leaves two thirds of the issue slots idle; run back to back they also push the whole Gram panel
-// (8 E bytes per candidate, 1.6 GB at 1M x 200) through HBM twice.  Here one persistent CTA per SM holds both: kFusedPairWarps
-// pair warps produce rows of K* into a two-slot ring of 32-candidate tiles in shared memory, kFusedPostWarps posterior
-// warps consume a tile as soon as its last row is written (DMMA triangular product, mean, EI) and release the slot;
-// K* never reaches global memory.  The two roles need different register budgets (72 / 120): the kernel is launched at
-// 80 registers per thread and the warp groups trade registers with setmaxnreg.
-constexpr int kFusedPairWarps = 20, kFusedPostWarps = 4, kFusedThreads = (kFusedPairWarps + kFusedPostWarps) * 32;
-constexpr int kFusedTC = 32;
-
-struct FusedLayout {
-  size_t off_ring, off_tiles, off_red, off_mus, total;
-  int tld, n_blk;
-};
-__host__ __device__ inline FusedLayout fused_layout(int n_eval, size_t pair_bytes) {
-  FusedLayout F;
-  F.tld = post_tile_ld(n_eval);
-  F.n_blk = (n_eval + kRowBlk - 1) / kRowBlk;
-  size_t o = align16(pair_bytes);
-  F.off_ring = o;   o += 64;
-  F.off_tiles = o;  o += sizeof(double) * 2 * (size_t)kFusedTC * F.tld;
-  F.off_red = o;    o += sizeof(double) * 2 * (size_t)F.n_blk * kFusedTC;
-  F.off_mus = o;    o += sizeof(double) * 2 * kFusedTC;
-  F.total = o;
-  return F;
-}
-
-// the posterior warps of the fused kernel: units of a tile = its 16-row blocks of L^-1 (largest first) + the mean dot
-// products, pulled from one shared queue; the warp that completes a tile runs its epilogue and releases the slot
-template <int TC, int kPD>
-__device__ __forceinline__ void posterior_consume(const PostParams& p, const TileRing ring, double* red, double* mus) {
-  constexpr int NB = TC / 8;
-  const int lane = threadIdx.x & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const int E = p.E, tld = ring.tld;
-  const int n_blk = (E + kRowBlk - 1) / kRowBlk, n_units = n_blk + 1, ks_max = (E + 3) >> 2;
-  const int64_t n_tiles = (p.n_cand + TC - 1) / TC;
-  const int n_my = blockIdx.x < n_tiles ? (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-  int* ctl = ring.ctl;
-  while (true) {
-    int w = 0;
-    if (lane == 0) w = atomicAdd(&ctl[kRingWork], 1);
-    w = __shfl_sync(0xffffffffu, w, 0);
-    const int i = w / n_units, u = w - i * n_units;
-    if (i >= n_my) break;
-    const int s = i & 1;
-    const int64_t c0 = ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * TC;
-    const int in_tile = (int)min((int64_t)TC, p.n_cand - c0);
-    // rows written into slot s so far (cumulative): every earlier tile of the slot was full
-    const int target = (i >> 1) * TC + in_tile;
-    if (lane == 0) {
-      while (*((volatile int*)&ctl[kRingFilled + s]) < target) __nanosleep(128);
-    }
-    __syncwarp();
-    __threadfence_block();
-    const double* Kt = ring.tiles + (size_t)s * TC * tld;
-    double* red_s = red + (size_t)s * n_blk * TC;
-    double* mus_s = mus + (size_t)s * TC;
-    if (u < n_blk) {
-      const int m = n_blk - 1 - u;  // largest block first
-      const int i0 = m * kRowBlk;
-      const int nks = min(i0 / 4 + 4, ks_max);
-      const int nks_up = min(i0 / 4 + 2, ks_max);
-      const bool lower_live = i0 + 8 < E;
-      double up[NB][2], lo[NB][2];
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) { up[nb][0] = up[nb][1] = 0.0; lo[nb][0] = lo[nb][1] = 0.0; }
-      const int KS = p.ldl >> 2;
-      const double* a_up = p.Linv + (size_t)(2 * m) * KS * 32 + lane;  // one coalesced 256-byte fragment per k-step
-      const double* a_lo = a_up + (size_t)KS * 32;
-      const double* bp = Kt + g * tld + t;
-      const int nks_pad = (nks + kPD - 1) & ~(kPD - 1);
-      double ra_up[kPD], ra_lo[kPD], bf[2][NB];
-#pragma unroll
-      for (int q = 0; q < kPD; ++q) {
-        ra_up[q] = __ldg(a_up + 32 * q);
-        ra_lo[q] = lower_live ? __ldg(a_lo + 32 * q) : 0.0;
-      }
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) bf[0][nb] = bp[(size_t)nb * 8 * tld];
-      const int n_full = nks & ~(kPD - 1);
-      for (int ks0 = 0; ks0 < n_full; ks0 += kPD) {
-#pragma unroll
-        for (int q = 0; q < kPD; ++q) {
-          const int ks = ks0 + q;
-          const double au = ra_up[q], al = ra_lo[q];
-          if (ks + kPD < nks_pad) {
-            ra_up[q] = __ldg(a_up + 32 * (ks + kPD));
-            ra_lo[q] = lower_live ? __ldg(a_lo + 32 * (ks + kPD)) : 0.0;
-          }
-#pragma unroll
-          for (int nb = 0; nb < NB; ++nb) bf[(q + 1) & 1][nb] = bp[(size_t)nb * 8 * tld + 4 * (ks + 1)];
-          if (ks < nks_up) {
-#pragma unroll
-            for (int nb = 0; nb < NB; ++nb) dmma8x8x4(up[nb][0], up[nb][1], au, bf[q & 1][nb]);
-          }
-          if (lower_live) {
-#pragma unroll
-            for (int nb = 0; nb < NB; ++nb) dmma8x8x4(lo[nb][0], lo[nb][1], al, bf[q & 1][nb]);
-          }
-        }
-      }
-      if (n_full < nks_pad) {  // the last, partly padded group: its padding steps load (finite or not) but never multiply
-#pragma unroll
-        for (int q = 0; q < kPD; ++q) {
-          const int ks = n_full + q;
-#pragma unroll
-          for (int nb = 0; nb < NB; ++nb) bf[(q + 1) & 1][nb] = bp[(size_t)nb * 8 * tld + 4 * (ks + 1)];
-          if (ks < nks_up) {
-#pragma unroll
-            for (int nb = 0; nb < NB; ++nb) dmma8x8x4(up[nb][0], up[nb][1], ra_up[q], bf[q & 1][nb]);
-          }
-          if (lower_live && ks < nks) {
-#pragma unroll
-            for (int nb = 0; nb < NB; ++nb) dmma8x8x4(lo[nb][0], lo[nb][1], ra_lo[q], bf[q & 1][nb]);
-          }
-        }
-      }
-      // column sums of squares over the 16 rows, reduced across the 8 row groups (lane bits 2..4)
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        double s0 = fma(up[nb][0], up[nb][0], lo[nb][0] * lo[nb][0]);
-        double s1 = fma(up[nb][1], up[nb][1], lo[nb][1] * lo[nb][1]);
-#pragma unroll
-        for (int o = 4; o < 32; o <<= 1) {
-          s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        }
-        if (g == 0) *reinterpret_cast<double2*>(&red_s[m * TC + nb * 8 + 2 * t]) = make_double2(s0, s1);
-      }
-    } else {
-      for (int c = lane >> 2; c < TC; c += 8) {
-        const int q = lane & 3;
-        double sacc = 0.0;
-        for (int j = q; j < E; j += 4) sacc = fma(Kt[c * tld + j], __ldg(&p.beta[j]), sacc);
-        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-        if (q == 0) mus_s[c] = sacc + p.mean_c;
-      }
-    }
-    __threadfence_block();
-    int d = 0;
-    if (lane == 0) d = atomicAdd(&ctl[kRingDone + s], 1);
-    d = __shfl_sync(0xffffffffu, d, 0);
-    if (d == n_units - 1) {  // this warp completed the tile: epilogue, then the slot is free for the pair warps again
-      __threadfence_block();
-      if (lane == 0) ctl[kRingDone + s] = 0;  // no unit of the slot's next tile can exist before the release below
-      for (int c = lane; c < in_tile; c += 32) {
-        double ss = 0.0;
-        for (int m = 0; m < n_blk; ++m) ss += red_s[m * TC + c];
-        const double var = p.variance - ss;
-        const double sg = sqrt(var);
-        const double mval = mus_s[c];
-        if (p.mu) p.mu[c0 + c] = mval;
-        if (p.sigma) p.sigma[c0 + c] = sg;
-        if (p.acq) {
-          double a;
-          if (p.acq_kind == BOSOT_ACQ_EI) {
-            const double dd = mval - *p.cur_max - p.xi;
-            const double z = dd / sg;
-            a = dd * norm_cdf(z) + sg * norm_pdf(z);
-          } else if (p.acq_kind == BOSOT_ACQ_UCB) {
-            a = mval + p.sqrt_ucb_beta * sg;
-          } else {
-            a = mval;
-          }
-          p.acq[c0 + c] = a;
-          if (p.peers) {
-#pragma unroll 1
-            for (int r = 0; r < p.n_peers; ++r) p.peers[r][p.peer_off + c0 + c] = a;
-          }
-        }
-      }
-      __syncwarp();
-      __threadfence_block();
-      if (lane == 0) atomicAdd(&ctl[kRingReleased + s], 1);
-    }
-  }
-}
-
-template <int R>
-__global__ void __launch_bounds__(kFusedThreads, 1)
-sot_fused_kernel(PairParams pp, bosot_grammar g, PostParams qp) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const int warp = threadIdx.x >> 5;
-  const StageLayout S = stage_layout(pp.L.e_pad, g.n_dim_cols, g.n_symbols, g.n_blocks);
-  const WarpLayout W = warp_layout(pp.L.e_pad, g.n_dim_cols, g.n_blocks, false);
-  const FusedLayout F = fused_layout(pp.L.n_eval, S.total + (size_t)kFusedPairWarps * W.total);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-  TileRing ring;
-  ring.ctl = reinterpret_cast<int*>(smem + F.off_ring);
-  ring.tiles = reinterpret_cast<double*>(smem + F.off_tiles);
-  ring.tld = F.tld;
-  ring.tc = kFusedTC;
-  if (threadIdx.x == 0) mbar_init(bar, 1);
-  if (threadIdx.x < 16) ring.ctl[threadIdx.x] = 0;
-  {  // tiles, partial sums and means start finite (the posterior reads padding columns and, in a last partial tile, unused rows)
-    double* z = ring.tiles;
-    const int n = (int)((F.total - F.off_tiles) / sizeof(double));
-    for (int x = threadIdx.x; x < n; x += kFusedThreads) z[x] = 0.0;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) pair_stage_tables(pp, g, smem, bar);
-  if (warp < kFusedPairWarps) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-    pair_body<R, false, kPairTiles>(pp, g, smem, bar, warp, kFusedPairWarps, ring);
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
-    posterior_consume<kFusedTC, 8>(qp, ring, reinterpret_cast<double*>(smem + F.off_red), reinterpret_cast<double*>(smem + F.off_mus));
   }
 }
 
 // scratch of one call = 16 bytes (the work counter of the pair launch) + the compact records
 constexpr size_t kScratchHead = 16;
 size_t pairs_scratch_bytes(int64_t n_cand) { return align16(kScratchHead + (size_t)n_cand * kScanBytes); }
-
-// launch 1 of the large-pool path: thread-per-tree scan -> compact records behind the 16-byte scratch head
-static int launch_scan(const uint8_t* d_trees, int64_t n_cand, int n_symbols, void* d_scratch, int32_t* d_status, int32_t* d_bad_zero,
-                       int dev, cudaStream_t stream) {
-  static std::atomic<bool> scan_attr[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
-  if (!(dev < 64 && scan_attr[dev])) {
-    if (int rc = cuda_check(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanThreads * kRecBytes),
-                            "cudaFuncSetAttribute(scan_kernel)")) return rc;
-    if (dev < 64) scan_attr[dev] = true;
-  }
-  const int64_t scan_blocks = (n_cand + kScanThreads - 1) / kScanThreads;
-  if (scan_blocks > 0x7fffffffLL) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: too many candidates");
-  scan_kernel<<<(unsigned)scan_blocks, kScanThreads, kScanThreads * kRecBytes, stream>>>(
-      d_trees, n_cand, n_symbols, static_cast<uint8_t*>(d_scratch) + kScratchHead, d_status, static_cast<unsigned long long*>(d_scratch), d_bad_zero);
-  return after_launch("scan_kernel");
-}
-
-// Pairs + posterior in one kernel (sot_fused_kernel) for a pool that is large enough for the scan launch and an
-// evaluated set whose tables and tile ring fit shared memory.  *used = false (and nothing launched) when the shape
-// does not qualify: the caller then takes the two-kernel route.
-int launch_acquire_fused(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar, const void* d_eval_blob, int n_eval,
-                         const double weights[3], double variance, double lengthscale, const double* d_Linv, int ldl,
-                         const double* d_beta, double mean_c, int acq_kind, const double* d_current_max, double xi, double ucb_beta,
-                         int32_t* d_status, void* d_scratch, size_t scratch_bytes, double* d_mu, double* d_sigma, double* d_acq,
-                         int32_t* d_bad, bool zero_bad, double* const* d_peers, int n_peers, int64_t peer_off, cudaStream_t stream,
-                         bool* used) {
-  *used = false;
-  if (experiment_flag() & 4) return BOSOT_OK;  // measurement switch: two-kernel route
-  if (!grammar || !d_eval_blob || !weights || !d_trees || !d_scratch || !d_Linv || !d_beta) return BOSOT_OK;  // let the plain route report it
-  if (n_cand <= kFusedScanMax || n_eval < 1 || n_eval > 32 * kMaxR) return BOSOT_OK;
-  if (ldl < n_eval || (ldl % kRowBlk) != 0 || scratch_bytes < pairs_scratch_bytes(n_cand) || (reinterpret_cast<uintptr_t>(d_scratch) & 15)) return BOSOT_OK;
-  if (acq_kind == BOSOT_ACQ_EI && d_acq && !d_current_max) return BOSOT_OK;
-  if (d_peers && (!d_acq || n_peers < 1 || n_peers > 64 || peer_off < 0)) return BOSOT_OK;
-  if (check_grammar(grammar) != BOSOT_OK) return BOSOT_OK;
-  const EvalLayout L = eval_layout(n_eval);
-  const StageLayout S = stage_layout(L.e_pad, grammar->n_dim_cols, grammar->n_symbols, grammar->n_blocks);
-  const WarpLayout W = warp_layout(L.e_pad, grammar->n_dim_cols, grammar->n_blocks, false);
-  const FusedLayout F = fused_layout(n_eval, S.total + (size_t)kFusedPairWarps * W.total);
-  const size_t smem_cap = 227 * 1024;
-  if (F.total > smem_cap) return BOSOT_OK;
-  int dev = 0, sms = 0;
-  if (int rc = cuda_check(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
-  if (int rc = cuda_check(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return rc;
-
-  PairParams p;
-  p.trees = d_trees; p.n_cand = n_cand; p.blob = static_cast<const uint8_t*>(d_eval_blob); p.L = L;
-  p.w_dim = weights[0]; p.w_path = weights[1]; p.w_sub = weights[2];
-  p.variance = variance; p.neg_inv_lsq = -1.0 / (lengthscale * lengthscale);
-  p.K = nullptr; p.D = nullptr; p.Df = nullptr; p.ld = F.tld;
-  p.next = static_cast<unsigned long long*>(d_scratch);
-  p.recs = static_cast<const uint8_t*>(d_scratch) + kScratchHead;
-  p.bad = d_bad; p.flags = 0; p.status = d_status; p.n_symbols = grammar->n_symbols;
-  PostParams q;
-  q.Kstar = nullptr; q.n_cand = n_cand; q.ld = F.tld; q.E = n_eval; q.ldl = ldl; q.Linv = d_Linv; q.beta = d_beta;
-  q.mean_c = mean_c; q.variance = variance; q.acq_kind = acq_kind; q.cur_max = d_current_max; q.xi = xi; q.sqrt_ucb_beta = sqrt(ucb_beta);
-  q.mu = d_mu; q.sigma = d_sigma; q.acq = d_acq; q.peers = d_peers; q.n_peers = d_peers ? n_peers : 0; q.peer_off = peer_off;
-
-  using FusedFn = void (*)(PairParams, bosot_grammar, PostParams);
-  static const FusedFn table[kMaxR] = {sot_fused_kernel<1>, sot_fused_kernel<2>, sot_fused_kernel<3>, sot_fused_kernel<4>,
-                                       sot_fused_kernel<5>, sot_fused_kernel<6>, sot_fused_kernel<7>, sot_fused_kernel<8>};
-  static std::atomic<bool> attr_set[64];
-  if (!(dev < 64 && attr_set[dev])) {
-    for (int r = 0; r < kMaxR; ++r)
-      if (int rc = cuda_check(cudaFuncSetAttribute(table[r], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
-                              "cudaFuncSetAttribute(sot_fused_kernel)")) return rc;
-    if (dev < 64) attr_set[dev] = true;
-  }
-  if (int rc = launch_scan(d_trees, n_cand, grammar->n_symbols, d_scratch, d_status, zero_bad ? d_bad : nullptr, dev, stream)) return rc;
-  const int64_t tiles = (n_cand + kFusedTC - 1) / kFusedTC;
-  const int R = (n_eval + 31) / 32;
-  table[R - 1]<<<(unsigned)(tiles < sms ? tiles : sms), kFusedThreads, F.total, stream>>>(p, *grammar, q);
-  if (int rc = after_launch("sot_fused_kernel")) return rc;
-  *used = true;
-  return BOSOT_OK;
-}
 
 int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar, const void* d_eval_blob,
                  int n_eval, const double weights[3], double variance, double lengthscale, double* d_K, double* d_D,
@@ -1188,7 +839,18 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
     pair_init_kernel<<<1, 32, 0, stream>>>(p.next, zero_bad ? d_bad : nullptr);
     if (int rc = after_launch("pair_init_kernel")) return rc;
   } else {
-    if (int rc = launch_scan(d_trees, n_cand, grammar->n_symbols, d_scratch, d_status, zero_bad ? d_bad : nullptr, dev, stream)) return rc;
+    // launch 1: scan
+    static std::atomic<bool> scan_attr[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
+    if (!(dev < 64 && scan_attr[dev])) {
+      if (int rc = cuda_check(cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanThreads * kRecBytes),
+                              "cudaFuncSetAttribute(scan_kernel)")) return rc;
+      if (dev < 64) scan_attr[dev] = true;
+    }
+    const int64_t scan_blocks = (n_cand + kScanThreads - 1) / kScanThreads;
+    if (scan_blocks > 0x7fffffffLL) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: too many candidates");
+    scan_kernel<<<(unsigned)scan_blocks, kScanThreads, kScanThreads * kRecBytes, stream>>>(
+        d_trees, n_cand, grammar->n_symbols, static_cast<uint8_t*>(d_scratch) + kScratchHead, d_status, p.next, zero_bad ? d_bad : nullptr);
+    if (int rc = after_launch("scan_kernel")) return rc;
   }
 
   // launch 2: pairs.  One persistent CTA per SM; small pools shrink the CTA so that every SM gets warps.
