@@ -114,6 +114,7 @@ class BayesianOptimizerObjects:
             and hasattr(self.candidate_generator, "search_space")
             and self.model.prediction_quantity == PredictionQuantity.PREDICT_F
             and not getattr(self.model.kernel, "transform_to_normal", False)
+            and self.model.has_constant_mean()
             and self.acquisition_function_type in (AcquisitionFunctionType.GP_UCB, AcquisitionFunctionType.EXPECTED_IMPROVEMENT)
         )
 
@@ -134,7 +135,7 @@ class BayesianOptimizerObjects:
     def acquisition_function(self, x_grid: List[object]) -> np.ndarray:
         """EI / GP-UCB / EI-per-second for every candidate (BOO:159-178), numpy fp64 [N]."""
         kind = self.acquisition_function_type
-        if self.model.prediction_quantity == PredictionQuantity.PREDICT_F and kind in (
+        if self.model.prediction_quantity == PredictionQuantity.PREDICT_F and self.model.has_constant_mean() and kind in (
             AcquisitionFunctionType.GP_UCB, AcquisitionFunctionType.EXPECTED_IMPROVEMENT, AcquisitionFunctionType.EXPECTED_IMPROVEMENT_PER_SECOND
         ):
             # fused device path: pairs -> Gram -> posterior -> acquisition in one pass over the candidates

@@ -171,6 +171,7 @@ class FlatEvolutionaryOptimizer:
         gen = self.generator
         population = torch.from_numpy(gen.get_initial_for_evolutionary_opt(self.population_size)).to(self.device)
         values = None
+        best_pinned = torch.zeros(2, dtype=torch.float64).pin_memory()
         for step in range(steps):
             if step > 0:
                 n_survive = int(self.population_size * self.survival_rate)
@@ -185,7 +186,9 @@ class FlatEvolutionaryOptimizer:
                                               torch.from_numpy(index), gen.grammar)
                 population = torch.cat([offspring, survivors])
             values = func(population).contiguous()
-            best = sot.argmax_first(values).cpu().numpy()
+            sot.argmax_first(values, out=best_pinned)  # 16 bytes written by the kernel into pinned host memory
+            torch.cuda.current_stream(self.device).synchronize()
+            best = best_pinned.numpy()
             fittest = int(best[1])
             if self.current_maximizer_value < best[0]:
                 self.current_maximizer_value = float(best[0])

@@ -117,7 +117,10 @@ class ObjectGpModel:
         assert len(flat) == y.shape[0]
         Df, state = self.kernel.fit_planes(flat)
         self.likelihood_variance = Parameter(np.power(self.observation_noise, 2.0), trainable=self.train_likelihood_variance)
-        self.model = dict(flat=flat, state=state, Df=Df, y=torch.from_numpy(y[:, 0].copy()).to(flat.trees.device))
+        # a mean that depends on the expression (BICMean) is split into its constant c and per-expression offsets: the
+        # device path sees targets y - offsets(X) and the constant mean c
+        y_eff = y[:, 0] - self._mean_offsets(flat)
+        self.model = dict(flat=flat, state=state, Df=Df, y=torch.from_numpy(np.ascontiguousarray(y_eff)).to(flat.trees.device))
         self._engine = None
 
     def infer(self, x_data, y_data: np.ndarray):
@@ -196,13 +199,18 @@ class ObjectGpModel:
         else:  # a kernel-kernel with a single distance plane (Hellinger)
             w3 = np.asarray(k.device_weights(), dtype=np.float64)
         Df, y = self.model["Df"], self.model["y"]
-        if getattr(self, "_fit_out", None) is None or self._fit_out.device != Df.device:
-            self._fit_out = torch.empty(9, dtype=torch.float64, device=Df.device)
+        # The nine results go straight into PINNED HOST memory: under unified addressing the kernel stores to the host
+        # pointer itself, so an evaluation is one launch + one stream synchronisation (no device buffer, no copy call).
+        if getattr(self, "_fit_out", None) is None:
+            self._fit_out = torch.zeros(9, dtype=torch.float64).pin_memory()
+            self._fit_out_np = self._fit_out.numpy()
+        stream = torch.cuda.current_stream(Df.device)
         with torch.cuda.device(Df.device):
             rc = _lib.load().bosot_gp_nll_grad(Df.data_ptr(), Df.shape[1], Df.stride(1), y.data_ptr(), (C.c_double * 3)(*w3), ls, var, noise, c,
-                                               self._fit_out.data_ptr(), torch.cuda.current_stream(Df.device).cuda_stream)
+                                               self._fit_out.data_ptr(), stream.cuda_stream)
         _lib.check(rc, "gp_nll_grad")
-        out = self._fit_out.cpu().numpy()
+        stream.synchronize()
+        out = self._fit_out_np.copy()
         if out[8] != 0.0:
             raise RuntimeError("Cholesky decomposition was not successful (leading minor %d not positive definite)" % int(out[8]))
         loss = float(out[0])
@@ -357,9 +365,19 @@ class ObjectGpModel:
             self._engine = (key, eng)
         return self._engine[1]
 
+    def _mean_offsets(self, flat) -> np.ndarray:
+        off = getattr(self.mean_function, "offsets", None)
+        return off(flat) if (self.use_mean_function and off is not None) else np.zeros(len(flat))
+
+    def has_constant_mean(self) -> bool:
+        """True when the prior mean is the same for every expression (the fused acquisition path assumes it)."""
+        return not (self.use_mean_function and hasattr(self.mean_function, "offsets"))
+
     def _posterior(self, x_test):
         flat = self.kernel.flatten(self.transform_input(x_test))
         mu, sigma, _ = self.engine().acquire_device(flat.trees)
+        if not self.has_constant_mean():
+            mu = mu + torch.from_numpy(self._mean_offsets(flat)).to(mu.device)
         return mu, sigma
 
     def predictive_dist(self, x_test) -> Tuple[np.ndarray, np.ndarray]:

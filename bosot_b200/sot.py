@@ -270,14 +270,16 @@ def topk(values: torch.Tensor, k: int, index_offset: int = 0, want_values: bool 
     return idx, vals
 
 
-def argmax_first(values: torch.Tensor, index_offset: int = 0) -> torch.Tensor:
-    """``np.argmax`` on the device (C-ABI ``bosot_argmax_f64``): float64 [2] = (max value, its FIRST index + offset)."""
+def argmax_first(values: torch.Tensor, index_offset: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``np.argmax`` on the device (C-ABI ``bosot_argmax_f64``): float64 [2] = (max value, its FIRST index + offset).
+    ``out`` may be a PINNED HOST tensor: the kernel then stores the pair straight into host memory (unified addressing)
+    and the caller only synchronises the stream."""
     _need_cuda(values, "values")
     if values.dtype != torch.float64 or values.dim() != 1 or not values.is_contiguous() or values.numel() < 1:
         raise ValueError("argmax_first takes a non-empty contiguous 1-D float64 tensor")
     lib = _lib.load()
     dev = values.device
-    out = torch.empty(2, dtype=torch.float64, device=dev)
+    out = out if out is not None else torch.empty(2, dtype=torch.float64, device=dev)
     work = torch.empty(lib.bosot_argmax_work_bytes(), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         rc = lib.bosot_argmax_f64(values.data_ptr(), values.numel(), int(index_offset), out.data_ptr(), work.data_ptr(), work.numel(), _stream(dev))
@@ -320,7 +322,8 @@ class AcquisitionEngine:
         self.state = state if state is not None else EvalState(eval_trees, grammar)
         self.n_eval = self.state.n_eval
         y = y.to(self.device, torch.float64).reshape(-1)
-        self.K_EE = sot_pairs(eval_trees, self.state, self.weights, self.variance, self.lengthscale)["K"]
+        # (the evaluated trees were validated when the state was built: no second status read-back here)
+        self.K_EE = sot_pairs(eval_trees, self.state, self.weights, self.variance, self.lengthscale, check=False)["K"]
         self.Linv, self.beta = gp_factorize(self.K_EE, self.noise_variance, y - self.mean_c)
         # posterior at the evaluated kernels -> current_max (bayesian_optimizer_objects.py:164-165)
         self.mu_data, self.sigma_data, _ = posterior_acq(self.K_EE, self.Linv, self.beta, self.mean_c, self.variance)

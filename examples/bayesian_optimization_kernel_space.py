@@ -48,6 +48,17 @@ optimizer.set_oracle(oracle)
 optimizer.set_candidate_generator(kernel_grammar_generator)
 optimizer.sample_train_set(24)
 metrics, queries, bests, _, t_iter, t_oracle, t_acq = optimizer.maximize(N_BO_STEPS)
+
+# the run's records, under the file names the reference writes (bosot/main.py:89-107,343-348)
+out_dir = os.environ.get("BOSOT_OUTPUT_DIR", os.path.join(os.path.dirname(os.path.abspath(__file__)), "output"))
+os.makedirs(out_dir, exist_ok=True)
+for pairs, list_name in ((queries, "QueryList"), (bests, "BestList")):
+    with open(os.path.join(out_dir, list_name + ".txt"), "w") as f:
+        for element, output in pairs:
+            f.write(str(element) + " value=" + str(output) + "\n")
+np.savetxt(os.path.join(out_dir, "iteration_time.txt"), np.array(t_iter))
+np.savetxt(os.path.join(out_dir, "oracle_time.txt"), np.array(t_oracle))
+np.savetxt(os.path.join(out_dir, "acquisition_time.txt"), np.array(t_acq))
 print("Best kernel:", optimizer.get_current_best())
 print("max observed: %.4f -> %.4f" % (metrics[0], metrics[-1]))
 print("acquisition time per BO step: %.1f ms (%d EI evaluations each)" % (1e3 * np.mean(t_acq), N_STEPS_EVOLUTIONARY_OPTIMIZER * POPULATION_EV_OPTIMIZER))

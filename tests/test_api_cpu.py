@@ -149,3 +149,42 @@ def test_bosot_alias_never_imports_a_module_twice():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
+
+
+def test_bic_mean_counts_parameters_like_the_reference():
+    """BICMean (reference object_mean_functions.py:51-74): m(x) = c - n_params(x) log(n) / n with n_params = sum of
+    tf.size over the trainable variables of the composed kernel: RBF 1 + nd, Linear 2, Periodic 2 + nd, RQ 2 + nd."""
+    from bosot_b200.kernels.kernel_grammar.kernel_grammar import (
+        ElementaryKernelGrammarExpression, KernelGrammarExpression, KernelGrammarOperator, SymbolicKernel)
+    from bosot_b200.models.object_mean_functions import BICMean, elementary_parameter_count
+
+    assert [elementary_parameter_count(n, 3) for n in ("RBFWithPrior_on_0", "LinearWithPrior_on_2", "PeriodicKernelWithPrior_on_1", "RQWithPrior_on_1")] == [2, 2, 3, 3]
+    assert [elementary_parameter_count(n, 3) for n in ("RBFWithPrior", "LinearWithPrior", "PeriodicKernelWithPrior")] == [4, 2, 5]
+
+    def leaf(name):
+        e = ElementaryKernelGrammarExpression(SymbolicKernel(name, 2))
+        e.set_generator_name("CKSWithRQSearchSpace")
+        return e
+
+    def node(op, a, b):
+        e = KernelGrammarExpression(a, b, KernelGrammarOperator[op])
+        e.set_generator_name("CKSWithRQSearchSpace")
+        return e
+
+    x = [leaf("LinearWithPrior_on_1"), node("ADD", node("MULTIPLY", leaf("RBFWithPrior_on_0"), leaf("RQWithPrior_on_1")), leaf("PeriodicKernelWithPrior_on_0"))]
+    m = BICMean(150, base_c=0.25)
+    np.testing.assert_allclose(m(x)[:, 0], 0.25 - np.array([2, 2 + 3 + 3]) * np.log(150.0) / 150.0, rtol=1e-15)
+    m2 = BICMean(150, divide_with_n_data=False)
+    np.testing.assert_allclose(m2(x)[:, 0], -np.array([2, 8]) * np.log(150.0), rtol=1e-15)
+    assert m.get_number_of_trainable_parameters(x[1].get_kernel()) == 8
+
+
+def test_config_picker_resolves_the_hot_path_configs():
+    from bosot_b200.configs.config_picker import ConfigPicker
+
+    assert ConfigPicker.pick_kernel_config("OTWeightedDimsExtendedGrammarKernelConfig")(input_dimension=2).input_dimension == 2
+    assert ConfigPicker.pick_model_config("BasicObjectGPModelConfig").__name__ == "BasicObjectGPModelConfig"
+    assert ConfigPicker.pick_bayesian_optimization_config("ObjectBOExpectedImprovementEAConfig")().population_evolutionary == 100
+    assert ConfigPicker.pick_kernel_grammar_generator_config("CKSHighDimGeneratorConfig")(input_dimension=5).input_dimension == 5
+    with pytest.raises(KeyError):
+        ConfigPicker.pick_kernel_config("NoSuchConfig")

@@ -376,3 +376,47 @@ def test_flat_and_object_evolutionary_modes_agree():
         runs.append([str(q) for q, _ in queries])
         assert all(q.get_generator_name() == "CKSWithRQSearchSpace" for q, _ in queries)
     assert runs[0] == runs[1], runs
+
+
+def test_bic_mean_in_the_model_and_the_bo_loop():
+    """A mean that depends on the expression (BICMean, reference object_mean_functions.py:51-74): the model subtracts
+    m(X) from the targets and adds m(x*) to the posterior mean; against the NumPy posterior with that mean, and one BO
+    step (which must leave the fused constant-mean acquisition path)."""
+    from bosot_b200.models.object_mean_functions import BICMean
+
+    gen_name, d = "CKSWithRQSearchSpace", 2
+    gen = GeneratorFactory.build(CKSWithRQGeneratorConfig(input_dimension=d))
+    np.random.seed(11)
+    x = gen.get_dataset_recursivly_generated(20, 1)
+    xs = gen.get_dataset_recursivly_generated(60, 1)
+    oracle = StructuralOracle([str(r) for r in gen.search_space.get_root_expressions()], seed=2)
+    y = np.array([[oracle.query(e)[0]] for e in x])
+    hyp = rn.Hyper(alphas=(0.5, 0.5, 0.5), lengthscale=1.0, variance=1.0, noise_variance=1e-4, mean_c=0.3)
+    mean = BICMean(150, base_c=hyp.mean_c)
+    model = ModelFactory.build(BasicObjectGPModelConfig(kernel_config=OTWeightedDimsExtendedGrammarKernelConfig(input_dimension=d),
+                                                        optimize_hps=False, prediction_quantity=PredictionQuantity.PREDICT_F))
+    model.set_mean_function(mean)
+    model.infer(x, y)
+    mu, sigma = model.predictive_dist(xs)
+    t = lambda xs_: [rn.parse_name(str(e)) for e in xs_]  # noqa: E731
+    K_EE, K_EN = rn.K(t(x), None, hyp, gen_name, d), rn.K(t(x), t(xs), hyp, gen_name, d)
+    m_tr, m_te = mean(x)[:, 0], mean(xs)[:, 0]
+    A = K_EE + hyp.noise_variance * np.eye(len(x))
+    mu_ref = K_EN.T @ np.linalg.solve(A, y[:, 0] - m_tr) + m_te
+    var_ref = hyp.variance - np.einsum("en,en->n", K_EN, np.linalg.solve(A, K_EN))
+    np.testing.assert_allclose(mu, mu_ref, rtol=1e-6, atol=1e-9)
+    ok = var_ref > 1e-9
+    np.testing.assert_allclose(sigma[ok], np.sqrt(var_ref[ok]), rtol=1e-5)
+    assert not model.has_constant_mean()
+    bo = BayesianOptimizerObjects(**ObjectBOExpectedImprovementEAConfig(n_steps_evolutionary=2, population_evolutionary=30).dict())
+    bo.set_model(model)
+    bo.set_oracle(oracle)
+    bo.set_candidate_generator(gen)
+    bo.set_train_set(list(x), y, [0.0] * len(x))
+    acq = bo.acquisition_function(xs)
+    mu_d, _ = model.predictive_dist(x)
+    dd = mu - np.max(mu_d) - 0.01
+    from scipy.stats import norm as _norm
+    np.testing.assert_allclose(acq[ok], (dd * _norm.cdf(dd / sigma) + sigma * _norm.pdf(dd / sigma))[ok], rtol=1e-9)
+    _, queries, *_ = bo.maximize(1)
+    assert len(queries) == 1
