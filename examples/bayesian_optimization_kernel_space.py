@@ -61,4 +61,4 @@ np.savetxt(os.path.join(out_dir, "oracle_time.txt"), np.array(t_oracle))
 np.savetxt(os.path.join(out_dir, "acquisition_time.txt"), np.array(t_acq))
 print("Best kernel:", optimizer.get_current_best())
 print("max observed: %.4f -> %.4f" % (metrics[0], metrics[-1]))
-print("acquisition time per BO step: %.1f ms (%d EI evaluations each)" % (1e3 * np.mean(t_acq), N_STEPS_EVOLUTIONARY_OPTIMIZER * POPULATION_EV_OPTIMIZER))
+print("acquisition time per BO step (median): %.1f ms (%d EI evaluations each)" % (1e3 * np.median(t_acq), N_STEPS_EVOLUTIONARY_OPTIMIZER * POPULATION_EV_OPTIMIZER))
