@@ -9,7 +9,7 @@
 // order is the portable choice, and the mirror of the object EA uses it too.)
 //
 // Two routes, no host synchronisation in either:
-//   n <= 16384 : ONE CTA sorts all (key, index) pairs in shared memory (bitonic network) and emits the last k;
+//   n <= 4096  : ONE CTA sorts all (key, index) pairs in shared memory (bitonic network) and emits the last k;
 //   larger n   : radix select on the order-preserving 64-bit image of the doubles (6 histogram passes of <= 11 bits, the
 //                last block of every pass picks the bin that holds the k-th largest), 3 more passes on the index among
 //                the values tied with the threshold when only part of them fits, one compaction, a chunk sort in shared
@@ -23,7 +23,8 @@ namespace bosot {
 constexpr int kTopkBins = 2048;
 constexpr int kTopkThreads = 512;
 constexpr int kTopkChunk = 2048;        // elements sorted per CTA in shared memory (radix route)
-constexpr int kTopkSmallMax = 16384;    // single-CTA route: 12 bytes of shared memory per element
+constexpr int kTopkSmallMax = 4096;     // single-CTA route (12 bytes of shared memory per element); the bitonic network of one CTA
+                                        // takes 290 us at 16384 elements (profiles/r2_ea_breakdown.txt), the radix route about 60
 
 __device__ __forceinline__ unsigned long long order_key(double v) {
   if (v != v) return ~0ULL;  // NaN sorts last (np.argsort)

@@ -57,8 +57,10 @@ def neighbour_at_index_host(record: np.ndarray, k: int, n_symbols: int) -> np.nd
     return out
 
 
-def neighbours_device(trees: torch.Tensor, index: torch.Tensor, grammar: Grammar, check: bool = True) -> torch.Tensor:
-    """``out[i]`` = neighbour number ``index[i]`` of ``trees[i]`` (C-ABI ``bosot_neighbours``)."""
+def neighbours_device(trees: torch.Tensor, index: torch.Tensor, grammar: Grammar, check: bool = True, status_out: Optional[list] = None) -> torch.Tensor:
+    """``out[i]`` = neighbour number ``index[i]`` of ``trees[i]`` (C-ABI ``bosot_neighbours``).  ``check`` reads the per-row
+    status back (one synchronisation); with ``check=False`` and a ``status_out`` list the status tensor is appended to it
+    for the caller to inspect at its next synchronisation point (``raise_on_neighbour_status``)."""
     if not trees.is_cuda:
         raise RuntimeError("bosot_b200: neighbours_device needs CUDA tensors (no CPU implementation on the product path)")
     n = trees.shape[0]
@@ -70,11 +72,19 @@ def neighbours_device(trees: torch.Tensor, index: torch.Tensor, grammar: Grammar
                                           torch.cuda.current_stream(trees.device).cuda_stream)
     _lib.check(rc, "neighbours")
     if check:
+        raise_on_neighbour_status([status])
+    elif status_out is not None:
+        status_out.append(status)
+    return out
+
+
+def raise_on_neighbour_status(statuses) -> None:
+    """Raise if any neighbour move of the collected launches failed (a move that would exceed the 63-node flat record)."""
+    for status in statuses:
         bad = torch.nonzero(status)
         if bad.numel():
             i = int(bad[0])
             raise ValueError("bosot_b200: neighbour move failed at row %d (code %d)" % (i, int(status[i])))
-    return out
 
 
 def _replay_global_rng(call, expected_outputs: int):
@@ -171,6 +181,7 @@ class FlatEvolutionaryOptimizer:
         gen = self.generator
         population = torch.from_numpy(gen.get_initial_for_evolutionary_opt(self.population_size)).to(self.device)
         values = None
+        statuses = []  # per-row status of every neighbour launch, inspected once at the end (no extra synchronisation per generation)
         best_pinned = torch.zeros(2, dtype=torch.float64).pin_memory()
         for step in range(steps):
             if step > 0:
@@ -183,7 +194,7 @@ class FlatEvolutionaryOptimizer:
                 # the host draws the neighbour numbers (np.random replay); it needs the node count of every survivor only
                 parent, index = gen.draw_offspring_indices(survivors[:, :1].cpu().numpy(), self.num_offspring)
                 offspring = neighbours_device(survivors[torch.from_numpy(parent).to(self.device)].contiguous(),
-                                              torch.from_numpy(index), gen.grammar)
+                                              torch.from_numpy(index), gen.grammar, check=False, status_out=statuses)
                 population = torch.cat([offspring, survivors])
             values = func(population).contiguous()
             sot.argmax_first(values, out=best_pinned)  # 16 bytes written by the kernel into pinned host memory
@@ -193,6 +204,7 @@ class FlatEvolutionaryOptimizer:
             if self.current_maximizer_value < best[0]:
                 self.current_maximizer_value = float(best[0])
                 self.current_maximizer = population[fittest].cpu().numpy()
+        raise_on_neighbour_status(statuses)
         return self.current_maximizer, self.current_maximizer_value
 
     def best_name(self) -> str:

@@ -174,30 +174,34 @@ class ObjectGpModel:
         return self._loss_and_grad_autograd(theta, layout)
 
     def _loss_and_grad_fused(self, theta: np.ndarray, layout) -> Tuple[float, np.ndarray]:
+        """One launch of ``bosot_gp_nll_grad`` + the chain rule of the parameter transforms.  Called ~50 times per model
+        update, so the host side is plain scalar Python (``math``), not NumPy: the transforms act on at most seven numbers."""
         import ctypes as C
+        import math
 
         k = self.kernel
+        th = [float(x) for x in theta]
         vals, pos = {}, 0
         for name, n in layout:
-            vals[name] = np.asarray(theta[pos : pos + n], dtype=np.float64)
+            vals[name] = th[pos : pos + n]
             pos += n
-        sig = lambda u: 1.0 / (1.0 + np.exp(-u))  # noqa: E731
+        softplus = lambda x: x if x > 30.0 else math.log1p(math.exp(x))  # noqa: E731
         has_alphas = hasattr(k, "alphas")
         if has_alphas:
-            alphas = sig(vals["alphas"]) if "alphas" in vals else np.asarray(k.alphas.numpy(), dtype=np.float64)
-        ls = float(_softplus(vals["lengthscale"])[0]) if "lengthscale" in vals else float(k.lengthscale)
-        var = float(_softplus(vals["variance"])[0]) if "variance" in vals else float(k.variance)
+            alphas = [1.0 / (1.0 + math.exp(-u)) for u in vals["alphas"]] if "alphas" in vals else [float(a) for a in np.ravel(k.alphas.numpy())]
+        ls = softplus(vals["lengthscale"][0]) if "lengthscale" in vals else float(k.lengthscale)
+        var = softplus(vals["variance"][0]) if "variance" in vals else float(k.variance)
         lo = LIKELIHOOD_VARIANCE_LOWER_BOUND
-        noise = float(_softplus(vals["noise"])[0]) + lo if "noise" in vals else float(self.likelihood_variance)
-        c = float(vals["c"][0]) if "c" in vals else self.mean_function.value()
+        noise = softplus(vals["noise"][0]) + lo if "noise" in vals else float(self.likelihood_variance)
+        c = vals["c"][0] if "c" in vals else self.mean_function.value()
         if has_alphas:
-            S = float(np.sum(alphas))
+            S = math.fsum(alphas)
             order = [_DEVICE_ORDER.index(f) for f in k.feature_type_list]
-            w3 = np.zeros(3)
+            w3 = [0.0, 0.0, 0.0]
             for g, a in zip(order, alphas):
                 w3[g] += a / S
         else:  # a kernel-kernel with a single distance plane (Hellinger)
-            w3 = np.asarray(k.device_weights(), dtype=np.float64)
+            w3 = [float(x) for x in k.device_weights()]
         Df, y = self.model["Df"], self.model["y"]
         # The nine results go straight into PINNED HOST memory: under unified addressing the kernel stores to the host
         # pointer itself, so an evaluation is one launch + one stream synchronisation (no device buffer, no copy call).
@@ -210,19 +214,19 @@ class ObjectGpModel:
                                                self._fit_out.data_ptr(), stream.cuda_stream)
         _lib.check(rc, "gp_nll_grad")
         stream.synchronize()
-        out = self._fit_out_np.copy()
+        out = self._fit_out_np.tolist()
         if out[8] != 0.0:
             raise RuntimeError("Cholesky decomposition was not successful (leading minor %d not positive definite)" % int(out[8]))
-        loss = float(out[0])
+        loss = out[0]
         d_w3, d_ls, d_var, d_noise, d_c = out[1:4], out[4], out[5], out[6], out[7]
         if self.set_prior_on_observation_noise:  # tfd.Exponential(rate) log-density on the constrained value
-            rate = 1.0 / np.power(self.expected_observation_noise, 2.0)
-            loss -= np.log(rate) - rate * noise
+            rate = 1.0 / (self.expected_observation_noise * self.expected_observation_noise)
+            loss -= math.log(rate) - rate * noise
             d_noise = d_noise + rate
         for pname, (mu, sd) in getattr(k, "hyperpriors", {}).items():  # LogNormal log-density on the constrained value
             x = ls if pname == "lengthscale" else var
-            loss -= -np.log(x * sd * np.sqrt(2.0 * np.pi)) - (np.log(x) - mu) ** 2 / (2.0 * sd * sd)
-            g = 1.0 / x + (np.log(x) - mu) / (sd * sd * x)
+            loss -= -math.log(x * sd * math.sqrt(2.0 * math.pi)) - (math.log(x) - mu) ** 2 / (2.0 * sd * sd)
+            g = 1.0 / x + (math.log(x) - mu) / (sd * sd * x)
             if pname == "lengthscale":
                 d_ls = d_ls + g
             else:
@@ -230,17 +234,17 @@ class ObjectGpModel:
         grads = []
         for name, n in layout:
             if name == "alphas":  # w_g = alpha_g / S, alpha = sigmoid(u)
-                d_alpha = (np.array([d_w3[g] for g in order]) - float(np.dot(d_w3, w3))) / S
-                grads.append(d_alpha * alphas * (1.0 - alphas))
+                dot = d_w3[0] * w3[0] + d_w3[1] * w3[1] + d_w3[2] * w3[2]
+                grads.extend((d_w3[g] - dot) / S * a * (1.0 - a) for g, a in zip(order, alphas))
             elif name == "lengthscale":
-                grads.append(np.array([d_ls * (1.0 - np.exp(-ls))]))
+                grads.append(d_ls * (1.0 - math.exp(-ls)))
             elif name == "variance":
-                grads.append(np.array([d_var * (1.0 - np.exp(-var))]))
+                grads.append(d_var * (1.0 - math.exp(-var)))
             elif name == "noise":
-                grads.append(np.array([d_noise * (1.0 - np.exp(-(noise - lo)))]))
+                grads.append(d_noise * (1.0 - math.exp(-(noise - lo))))
             else:
-                grads.append(np.array([d_c]))
-        return loss, (np.concatenate(grads) if grads else np.zeros(0))
+                grads.append(d_c)
+        return loss, np.array(grads, dtype=np.float64)
 
     def _loss_and_grad_autograd(self, theta: np.ndarray, layout) -> Tuple[float, np.ndarray]:
         dev = self.model["Df"].device

@@ -273,7 +273,7 @@ int bosot_acquire_host_scatter(const uint8_t* h_trees, int64_t n_cand, const bos
  * bosot_topk_f64: d_out_index[j] (int64, + index_offset) / d_out_value[j] (may be NULL), j = 0 .. k-1, are the last k
  * entries of the ascending order by (value, index) = np.argsort(values, kind="stable")[n-k:]; NaN sorts above +inf
  * like NumPy, -0.0 == +0.0.  1 <= k <= n < 2^31.  d_work: bosot_topk_work_bytes(n, k) bytes, 16-byte aligned
- * (not touched when n <= 16384: one CTA sorts in shared memory).  No host synchronisation.
+ * (not touched when n <= 4096: one CTA sorts in shared memory).  No host synchronisation.
  * bosot_argmax_f64: d_out2[0] = max value, d_out2[1] = its FIRST index (+ index_offset) as a double (np.argmax: a NaN
  * counts as the maximum).  d_work: bosot_argmax_work_bytes() bytes (used when n > 65536). */
 size_t bosot_topk_work_bytes(int64_t n, int64_t k);
