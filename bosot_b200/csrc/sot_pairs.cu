@@ -33,6 +33,7 @@
 #include "sot_common.cuh"
 #include "launch.cuh"
 #include "fast_math.cuh"
+#include "exp_table.cuh"
 
 namespace bosot {
 
@@ -67,6 +68,7 @@ struct PairParams {
   EvalLayout L;
   double w_dim, w_path, w_sub;
   double variance, neg_inv_lsq;  // -1 / lengthscale^2
+  double a_dim, a_path, a_sub;   // w_f * (-1 / lengthscale^2): the Gram argument is formed as one fused sum (kFast)
   double* K;
   double* D;
   double* Df;
@@ -104,10 +106,10 @@ __host__ __device__ inline WarpLayout warp_layout(int e_pad, int n_dim_cols, int
 // The DIM_WISE section holds either the block-state tables (stateP + sid8T) or, when a block has more than
 // kMaxStates distinct vectors, the dense transposed matrix; it is sized for the larger of the two.
 struct StageLayout {
-  size_t off_meta, off_dim, off_sid, off_flat, off_rsub, off_rpath, off_symT2, off_nn2, off_nn, off_nl, total;
-  uint32_t b_meta, b_state, b_sid, b_flat, b_dimT, b_r, b_symT2, b_nn2, b_n;
+  size_t off_meta, off_dim, off_sid, off_flat, off_rsub, off_rpath, off_symT2, off_nn2, off_nn, off_nl, off_exp, total;
+  uint32_t b_meta, b_state, b_sid, b_flat, b_dimT, b_r, b_symT2, b_nn2, b_n, b_exp;
 };
-__host__ __device__ inline StageLayout stage_layout(int e_pad, int n_dim_cols, int n_symbols, int n_blocks) {
+__host__ __device__ inline StageLayout stage_layout(int e_pad, int n_dim_cols, int n_symbols, int n_blocks, bool fast_exp) {
   StageLayout S;
   S.b_meta = (uint32_t)sizeof(DimMeta);
   S.b_state = (uint32_t)(sizeof(double) * (size_t)n_dim_cols * kMaxStates);
@@ -128,6 +130,9 @@ __host__ __device__ inline StageLayout stage_layout(int e_pad, int n_dim_cols, i
   S.off_nn2 = o;   o += S.b_nn2;
   S.off_nn = o;    o += S.b_n;
   S.off_nl = o;    o += S.b_n;
+  o = align16(o);
+  S.b_exp = fast_exp ? (uint32_t)(sizeof(double) * kExpTableSize) : 0u;
+  S.off_exp = o;   o += S.b_exp;
   S.total = align16(o);
   return S;
 }
@@ -427,14 +432,57 @@ __device__ __forceinline__ void exp_nonpos_group(double (&x)[G]) {
   }
 }
 
+// Table-driven exp for the launches whose hyper-parameters bound the Gram argument (launch_pairs: -600 <= x <= 0, all
+// weights >= 0, variance in [2^-100, 2^100]): x = (1024 n + j) ln2 / 1024 + r with |r| <= ln2 / 2048, so
+//   variance * exp(x) = 2^n * (variance * 2^(j/1024)) * (1 + r + r^2/2 + r^3/6 + r^4/24)      (r^5/120 < 4e-20)
+// with the 1024 values variance * 2^(j/1024) in shared memory (exp_table.cuh, scaled once per CTA).  No clamp and
+// no two-step scaling: the result is a normal number, so 2^n is one integer add on the exponent field.  9 fp64
+// operations per value instead of 21; at most 0.93 ulp off exp(x) before the variance (checked against 50-digit
+// arithmetic, gen_exp_table.py), exactly `variance` at x = 0.
+__constant__ double c_fexp[6] = {
+    1477.3197218702985,              // [0] 1024 / ln 2
+    6755399441055744.0,              // [1] 1.5 * 2^52
+    -0x1.62e42fee00000p-11,          // [2] -ln2 / 1024, high part (32 significant bits: n * high is exact for |n| < 2^21)
+    -0x1.a39ef35793c76p-43,          // [3] -ln2 / 1024, low part
+    1.0 / 24.0, 1.0 / 6.0};
+template <int G>
+__device__ __forceinline__ void exp_table_group(double (&x)[G], const uint8_t* __restrict__ tab) {
+  const double c = c_fexp[0], magic = c_fexp[1], hi = c_fexp[2], lo = c_fexp[3], c24 = c_fexp[4], c6 = c_fexp[5];
+  double r[G], tj[G];
+  int m[G];
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    const double t = fma(x[i], c, magic);
+    m[i] = __double2loint(t);
+    const double nf = t - magic;
+    r[i] = fma(nf, lo, fma(nf, hi, x[i]));
+    tj[i] = *reinterpret_cast<const double*>(tab + ((m[i] << 3) & (8 * (kExpTableSize - 1))));
+  }
+#pragma unroll
+  for (int i = 0; i < G; ++i) {
+    double q = fma(r[i], c24, c6);
+    q = fma(q, r[i], 0.5);
+    q = fma(q, r[i], 1.0);
+    const double v = fma(tj[i] * r[i], q, tj[i]);
+    x[i] = __hiloint2double(__double2hiint(v) + ((m[i] & ~(kExpTableSize - 1)) << (20 - kExpTableBits)), __double2loint(v));
+  }
+}
+
+// a << n with PTX semantics (shift amounts beyond 31 give 0; in C++ they are undefined)
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t a, uint32_t n) {
+  uint32_t r;
+  asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(n));
+  return r;
+}
+
 // exact uint32 -> double for m < 2^32 without the conversion pipe: 2^52 + m is exact, subtract 2^52
 __device__ __forceinline__ double u32_to_f64(uint32_t m) {
   return __hiloint2double(0x43300000, (int)m) - 4503599627370496.0;
 }
 
 // R: evaluated trees per lane per tile; kExtra: also write D and/or Df; kFused: no scan launch in front, every warp scans
-// its candidate itself (warp_scan_tree) straight from the flat records
-template <int R, bool kExtra, bool kFused>
+// its candidate itself (warp_scan_tree) straight from the flat records; kFast: bounded Gram argument (exp_table_group)
+template <int R, bool kExtra, bool kFused, bool kFast>
 __global__ void __launch_bounds__(kMaxPairWarps * 32, 1)
 sot_pair_kernel(PairParams p, bosot_grammar g) {
   constexpr int RP = (R + 1) / 2;  // packed pairs of evaluated trees per lane
@@ -451,13 +499,13 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   pdl_launch_dependents();  // a posterior launch behind this one may set up its shared memory early (it waits before reading K*)
   // ---- stage the evaluated set's dense tables once per (persistent) CTA: TMA bulk copies -> mbarrier
   // (the blob is the product of an OLDER launch than the scan in front of this one, so this may run before pdl_wait())
-  const StageLayout S = stage_layout(e_pad, g.n_dim_cols, g.n_symbols, g.n_blocks);
+  const StageLayout S = stage_layout(e_pad, g.n_dim_cols, g.n_symbols, g.n_blocks, kFast);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   if (threadIdx.x == 0) mbar_init(bar, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
     const int states = __ldg(reinterpret_cast<const int*>(p.blob + p.L.off_meta));  // DimMeta::use_states
-    mbar_expect_tx(bar, S.b_meta + (states ? S.b_state + S.b_sid + S.b_flat : S.b_dimT) + 2 * S.b_r + S.b_symT2 + S.b_nn2 + 2 * S.b_n);
+    mbar_expect_tx(bar, S.b_meta + (states ? S.b_state + S.b_sid + S.b_flat : S.b_dimT) + 2 * S.b_r + S.b_symT2 + S.b_nn2 + 2 * S.b_n + S.b_exp);
     tma_bulk_g2s(smem + S.off_meta, p.blob + p.L.off_meta, S.b_meta, bar);
     if (states) {
       tma_bulk_g2s(smem + S.off_dim, p.blob + p.L.off_stateP, S.b_state, bar);
@@ -472,6 +520,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     tma_bulk_g2s(smem + S.off_nn2, p.blob + p.L.off_nn2, S.b_nn2, bar);
     tma_bulk_g2s(smem + S.off_nn, p.blob + p.L.off_nnodes, S.b_n, bar);
     tma_bulk_g2s(smem + S.off_nl, p.blob + p.L.off_nleaves, S.b_n, bar);
+    if (kFast) tma_bulk_g2s(smem + S.off_exp, g_exp2_table, S.b_exp, bar);
   }
   const DimMeta* meta = reinterpret_cast<const DimMeta*>(smem + S.off_meta);
   const double* stateP = reinterpret_cast<const double*>(smem + S.off_dim);  // [n_pcols][kMaxStates]   (state mode)
@@ -484,6 +533,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   const uint32_t* e_nn2 = reinterpret_cast<const uint32_t*>(smem + S.off_nn2);
   const uint8_t* e_nn = smem + S.off_nn;
   const uint8_t* e_nl = smem + S.off_nl;
+  const uint8_t* exp_tab = smem + S.off_exp;  // kFast: variance * 2^(j/1024)
 
   const WarpLayout W = warp_layout(e_pad, g.n_dim_cols, g.n_blocks, kFused);
   uint8_t* wbase = smem + S.total + (size_t)warp * W.total;
@@ -531,6 +581,19 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     else nxt = load_slice(t);
   }
   mbar_wait(bar, 0);  // tables landed (the copy overlapped the first record load)
+  if (kFast) {        // fold the variance into the exp table (the entry of x = 0 becomes exactly `variance`)
+    double* tv = reinterpret_cast<double*>(smem + S.off_exp);
+    const int nt = blockDim.x;  // 32 .. 896 threads (a small pool runs one warp per CTA: eight entries in flight per thread)
+#pragma unroll 1
+    for (int i = threadIdx.x; i < kExpTableSize; i += 8 * nt) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (i + u * nt < kExpTableSize) ? tv[i + u * nt] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) if (i + u * nt < kExpTableSize) tv[i + u * nt] = v[u] * p.variance;
+    }
+    __syncthreads();
+  }
   const bool use_states = meta->use_states != 0;
   const int n_flat = meta->n_flat;
 
@@ -575,7 +638,8 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
 
     __syncwarp();  // acc[] is all zero here: zeroed before the loop, and every entry is cleared again by the epilogue that reads it
 #pragma unroll 1
-    for (int s = lane; s < BOSOT_MAX_SYMBOLS + BOSOT_MAX_BLOCKS; s += 32) scnt[s] = 0u;
+    for (int s = lane; s < g.n_symbols; s += 32) scnt[s] = 0u;  // only the grammar's symbols / blocks are ever read
+    if (lane < g.n_blocks) btot[lane] = 0u;
     __syncwarp();
 
     // leaves: symbol multiplicities (SUBTREES leaf classes, DIM_WISE) and PATHS (key = symbol * 64 + code)
@@ -644,20 +708,21 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
       const unsigned ne_mask = __ballot_sync(full, ne);
       if (ne) slot[__popc(ne_mask & lt_mask)] = make_uint2(r.x - start, cnt_a);
       __syncwarp();
+      const uint32_t startx = ne ? start : 0x80000000u;  // empty segments never start inside a round
       uint32_t before = 0u;  // segments that start before this round
 #pragma unroll 1
       for (uint32_t q0 = 0; q0 < total; q0 += 32) {
-        const uint32_t rel = start - q0;
-        const uint32_t m = __reduce_or_sync(full, (ne && rel < 32u) ? (1u << rel) : 0u);
+        const uint32_t m = __reduce_or_sync(full, shl_clamp(1u, startx - q0));  // shl.b32: 0 for shift amounts >= 32
         const uint32_t ord = before + (uint32_t)__popc(m & le_mask) - 1u;
         before += (uint32_t)__popc(m);
         const uint32_t q = q0 + lane;
-        if (q < total) {
-          const uint2 sl = slot[ord];
-          const uint32_t pq = __ldg(&post[sl.x + q]);
-          const uint32_t e = pq & 0xffffu, cb = (pq >> 16) & 0xffu, Tb = pq >> 24;
-          atomicAdd(&acc[e], min(sl.y * Tb, cb * Ta) << shift);
-        }
+        // the lanes past the end of the list (last round only) read on into the blob (the postings are followed by
+        // the other tables of the evaluated set) and drop what they read: cheaper than a divergent branch per round
+        const uint2 sl = slot[ord];
+        const uint32_t pq = __ldg(&post[sl.x + q]);
+        const uint32_t e = pq & 0xffffu, cb = (pq >> 16) & 0xffu, Tb = pq >> 24;
+        const uint32_t contrib = min(sl.y * Tb, cb * Ta) << shift;
+        if (q < total) atomicAdd(&acc[e], contrib);
       }
       __syncwarp();
     };
@@ -670,10 +735,15 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
       for (int k = lane; k < n_flat; k += 32) {
         const uint32_t dsc = flat[k];
         const int j1 = (dsc >> 8) & 0xff, ts = dsc >> 16;
-        const double* sv = stateP + (ts & (kMaxStates - 1));
+        const int j0 = dsc & 0xff;
+        const double* sv = stateP + (ts & (kMaxStates - 1)) + j0 * kMaxStates;
+        const double* av = avec + j0;
         double sum = 0.0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)  // a block has 1 + kinds columns, four at most in the reference's search spaces
+          if (j0 + u < j1) sum += fabs(av[u] - sv[u * kMaxStates]);
 #pragma unroll 1
-        for (int j = dsc & 0xff; j < j1; ++j) sum += fabs(avec[j] - sv[j * kMaxStates]);
+        for (int j = j0 + 4; j < j1; ++j) sum += fabs(avec[j] - stateP[(ts & (kMaxStates - 1)) + j * kMaxStates]);
         tab[ts] = sum;
       }
     }
@@ -754,23 +824,29 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
             // when the histograms coincide (like the reference), and (1/Ta)(1/Tb) first keeps D(a,b) == D(b,a) bitwise
             const double d_sub = u32_to_f64((uint32_t)nn * tb_sub - m_sub) * (rTa2_sub * rsp[32 * r]);
             const double d_path = u32_to_f64((uint32_t)nl * tb_path - m_path) * (rTa2_path * rpp[32 * r]);
-            // sum_f w_f * D_f in feature_type_list order (kernel_kernel_grammar_tree.py:159-161)
-            const double d = __dadd_rn(__dadd_rn(__dmul_rn(p.w_dim, ddim[r]), __dmul_rn(p.w_path, d_path)),
-                                       __dmul_rn(p.w_sub, d_sub));
-            if (kExtra) {
-              const int e = eb + 32 * r;
-              if (e < E) {
-                if (p.Df) { p.Df[row + e] = ddim[r]; p.Df[plane + row + e] = d_path; p.Df[2 * plane + row + e] = d_sub; }
-                if (p.D) p.D[row + e] = d;
+            if (kExtra || !kFast) {
+              // sum_f w_f * D_f in feature_type_list order (kernel_kernel_grammar_tree.py:159-161)
+              const double d = __dadd_rn(__dadd_rn(__dmul_rn(p.w_dim, ddim[r]), __dmul_rn(p.w_path, d_path)),
+                                         __dmul_rn(p.w_sub, d_sub));
+              if (kExtra) {
+                const int e = eb + 32 * r;
+                if (e < E) {
+                  if (p.Df) { p.Df[row + e] = ddim[r]; p.Df[plane + row + e] = d_path; p.Df[2 * plane + row + e] = d_sub; }
+                  if (p.D) p.D[row + e] = d;
+                }
               }
+              x[i] = d * p.neg_inv_lsq;
             }
-            x[i] = d * p.neg_inv_lsq;
+            // bounded hyper-parameters: the Gram argument -d / l^2 as one fused sum of the three terms (same value for
+            // (a, b) and (b, a), exactly -0 for coinciding histograms)
+            if (kFast) x[i] = fma(p.a_sub, d_sub, fma(p.a_path, d_path, p.a_dim * ddim[r]));
           } else {
             x[i] = 0.0;
           }
         }
         if (p.K) {
-          exp_nonpos_group<kG>(x);
+          if (kFast) exp_table_group<kG>(x, exp_tab);  // variance included
+          else exp_nonpos_group<kG>(x);
 #pragma unroll
           for (int i = 0; i < kG; ++i)  // pin the results here: otherwise every chain is sunk into its own guarded store
             if (r0 + i < R) asm volatile("" : "+d"(x[i]));
@@ -778,10 +854,11 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
           for (int i = 0; i < kG; ++i) {
             const int r = r0 + i, e = eb + 32 * r;
             if (r < R) {
+              const double kv = kFast ? x[i] : p.variance * x[i];
               // R = ceil(E / 32) when there is one tile (R < kMaxR): every row but the last lies inside E
-              if (R < kMaxR && r < R - 1) p.K[row + e] = p.variance * x[i];
+              if (R < kMaxR && r < R - 1) p.K[row + e] = kv;
               // padding columns of the Gram row stay finite (the posterior kernel may read them)
-              else if (e < ld_i) p.K[row + e] = e < E ? p.variance * x[i] : 0.0;
+              else if (e < ld_i) p.K[row + e] = e < E ? kv : 0.0;
             }
           }
         }
@@ -817,6 +894,16 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   p.w_sub = weights[2];
   p.variance = variance;
   p.neg_inv_lsq = -1.0 / (lengthscale * lengthscale);
+  p.a_dim = p.w_dim * p.neg_inv_lsq;
+  p.a_path = p.w_path * p.neg_inv_lsq;
+  p.a_sub = p.w_sub * p.neg_inv_lsq;
+  // Bounded Gram argument?  Every per-feature distance lies in [0, 2] (DIM_WISE: in [0, 2] per block), so with
+  // non-negative weights -d / l^2 >= -2 (n_blocks w_dim + w_path + w_sub) / l^2; when that is above -600 and the
+  // variance is an ordinary number, exp needs neither a clamp nor a denormal path (exp_table_group).  Anything else
+  // (negative or non-finite weights, extreme length scales) takes the general exp_nonpos route.
+  const double x_min = 2.0 * (grammar->n_blocks * p.w_dim + p.w_path + p.w_sub) * p.neg_inv_lsq;
+  const bool fast = p.w_dim >= 0.0 && p.w_path >= 0.0 && p.w_sub >= 0.0 && x_min >= -600.0 && x_min <= 0.0 &&
+                    variance >= 0x1p-100 && variance <= 0x1p100 && !(experiment_flag() & 4);
   p.K = d_K;
   p.D = d_D;
   p.Df = d_Df;
@@ -856,7 +943,7 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   // launch 2: pairs.  One persistent CTA per SM; small pools shrink the CTA so that every SM gets warps.
   int warps = kMaxPairWarps;
   while (warps > 1 && (n_cand + warps - 1) / warps < sms) warps >>= 1;
-  const StageLayout S = stage_layout(p.L.e_pad, grammar->n_dim_cols, grammar->n_symbols, grammar->n_blocks);
+  const StageLayout S = stage_layout(p.L.e_pad, grammar->n_dim_cols, grammar->n_symbols, grammar->n_blocks, fast);
   const size_t per_warp = warp_layout(p.L.e_pad, grammar->n_dim_cols, grammar->n_blocks, fused).total;
   const size_t smem_cap = 220 * 1024;
   size_t smem = S.total + (size_t)warps * per_warp;
@@ -870,16 +957,18 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   const int rounds = (n_eval + 31) / 32;  // evaluated trees per lane; beyond 256 trees: tiles of 256 (e_pad is a multiple of 256)
   const int R = rounds < kMaxR ? rounds : kMaxR;
   using KernelFn = void (*)(PairParams, bosot_grammar);
-#define BOSOT_PAIR_ROW(r) {{sot_pair_kernel<r, false, false>, sot_pair_kernel<r, false, true>}, {sot_pair_kernel<r, true, false>, sot_pair_kernel<r, true, true>}}
-  static const KernelFn table[kMaxR][2][2] = {BOSOT_PAIR_ROW(1), BOSOT_PAIR_ROW(2), BOSOT_PAIR_ROW(3), BOSOT_PAIR_ROW(4),
-                                              BOSOT_PAIR_ROW(5), BOSOT_PAIR_ROW(6), BOSOT_PAIR_ROW(7), BOSOT_PAIR_ROW(8)};
+#define BOSOT_PAIR_X(r, x, f) {sot_pair_kernel<r, x, f, false>, sot_pair_kernel<r, x, f, true>}
+#define BOSOT_PAIR_ROW(r) {{BOSOT_PAIR_X(r, false, false), BOSOT_PAIR_X(r, false, true)}, {BOSOT_PAIR_X(r, true, false), BOSOT_PAIR_X(r, true, true)}}
+  static const KernelFn table[kMaxR][2][2][2] = {BOSOT_PAIR_ROW(1), BOSOT_PAIR_ROW(2), BOSOT_PAIR_ROW(3), BOSOT_PAIR_ROW(4),
+                                                 BOSOT_PAIR_ROW(5), BOSOT_PAIR_ROW(6), BOSOT_PAIR_ROW(7), BOSOT_PAIR_ROW(8)};
 #undef BOSOT_PAIR_ROW
-  KernelFn kernel = table[R - 1][extra ? 1 : 0][fused ? 1 : 0];
+#undef BOSOT_PAIR_X
+  KernelFn kernel = table[R - 1][extra ? 1 : 0][fused ? 1 : 0][fast ? 1 : 0];
   static std::atomic<bool> attr_set[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
   if (!(dev < 64 && attr_set[dev])) {
     for (int r = 0; r < kMaxR; ++r)
-      for (int x = 0; x < 4; ++x)
-        if (int rc = cuda_check(cudaFuncSetAttribute(table[r][x >> 1][x & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
+      for (int x = 0; x < 8; ++x)
+        if (int rc = cuda_check(cudaFuncSetAttribute(table[r][x >> 2][(x >> 1) & 1][x & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
                                 "cudaFuncSetAttribute(sot_pair_kernel)")) return rc;
     if (dev < 64) attr_set[dev] = true;
   }
