@@ -81,6 +81,16 @@ SIGNATURES = {
         C.c_int,
         [_P, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, _P, C.c_double, C.c_double, C.c_int, _P, C.c_double, C.c_double, _P, _P, _P, _P],
     ),
+    "bosot_sot_pairs_f32": (C.c_int, [_P, C.c_int64, _G, _P, C.c_int, _D3, C.c_double, C.c_double, _P, _P, _P, C.c_int64, _P, _P, C.c_size_t, _P]),
+    "bosot_posterior_acq_f32": (
+        C.c_int,
+        [_P, C.c_int64, C.c_int64, C.c_int, _P, C.c_int, _P, C.c_double, C.c_double, C.c_int, _P, C.c_double, C.c_double, _P, _P, _P, _P],
+    ),
+    "bosot_acquire_device_f32": (
+        C.c_int,
+        [_P, C.c_int64, _G, _P, C.c_int, _D3, C.c_double, C.c_double, _P, C.c_int, _P, C.c_double, C.c_int, _P, C.c_double, C.c_double,
+         _P, C.c_size_t, _P, _P, _P, _P, _P],
+    ),
     "bosot_pack_linv": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P]),
     "bosot_max_f64": (C.c_int, [_P, C.c_int64, _P, _P]),
     "bosot_acquire_work_bytes": (C.c_size_t, [C.c_int64, C.c_int]),

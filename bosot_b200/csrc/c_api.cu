@@ -55,12 +55,12 @@ int check_grammar(const bosot_grammar* g) {
 int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar, const void* d_eval_blob,
                  int n_eval, const double weights[3], double variance, double lengthscale, double* d_K, double* d_D,
                  double* d_Df, int64_t ld, int32_t* d_status, void* d_scratch, size_t scratch_bytes, cudaStream_t stream,
-                 int32_t* d_bad, bool zero_bad);
+                 int32_t* d_bad, bool zero_bad, bool f32 = false);
 size_t pairs_scratch_bytes(int64_t n_cand);
 int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval, const double* d_Linv, int ldl,
                      const double* d_beta, double mean_c, double variance, int acq_kind, const double* d_current_max,
                      double xi, double ucb_beta, double* d_mu, double* d_sigma, double* d_acq, cudaStream_t stream,
-                     double* const* d_peers = nullptr, int n_peers = 0, int64_t peer_off = 0);
+                     double* const* d_peers = nullptr, int n_peers = 0, int64_t peer_off = 0, bool f32 = false);
 
 // work buffer of the composed calls:  K*[n_cand][ld] | trees[n_cand][64] | mu | sigma | acq | status | bad count | scan records
 struct WorkLayout {
@@ -97,6 +97,15 @@ extern "C" int bosot_posterior_acq(const double* d_Kstar, int64_t n_cand, int64_
                                    double* d_mu, double* d_sigma, double* d_acq, void* stream) {
   return launch_posterior(d_Kstar, n_cand, ld, n_eval, d_Linv, ldl, d_beta, mean_c, variance, acq_kind, d_current_max,
                           xi, ucb_beta, d_mu, d_sigma, d_acq, (cudaStream_t)stream);
+}
+
+extern "C" int bosot_posterior_acq_f32(const float* d_Kstar, int64_t n_cand, int64_t ld, int n_eval,
+                                       const double* d_Linv, int ldl, const double* d_beta, double mean_c, double variance,
+                                       int acq_kind, const double* d_current_max, double xi, double ucb_beta,
+                                       float* d_mu, float* d_sigma, float* d_acq, void* stream) {
+  return launch_posterior(reinterpret_cast<const double*>(d_Kstar), n_cand, ld, n_eval, d_Linv, ldl, d_beta, mean_c, variance,
+                          acq_kind, d_current_max, xi, ucb_beta, reinterpret_cast<double*>(d_mu), reinterpret_cast<double*>(d_sigma),
+                          reinterpret_cast<double*>(d_acq), (cudaStream_t)stream, nullptr, 0, 0, true);
 }
 
 extern "C" int bosot_posterior_acq_scatter(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval,
@@ -204,7 +213,7 @@ static int acquire_on_device(const char* who, const uint8_t* d_trees, int64_t n_
                              const double* d_Linv, int ldl, const double* d_beta, double mean_c, int acq_kind,
                              const double* d_current_max, double xi, double ucb_beta, void* d_work, size_t work_bytes,
                              double* d_mu, double* d_sigma, double* d_acq, int32_t* d_n_bad,
-                             double* const* d_peers, int n_peers, int64_t peer_off, cudaStream_t st) {
+                             double* const* d_peers, int n_peers, int64_t peer_off, cudaStream_t st, bool f32 = false) {
   char msg[128];
   if (!d_work) { std::snprintf(msg, sizeof(msg), "%s: null work buffer", who); return set_error(BOSOT_EINVAL, msg); }
   if (n_cand < 0 || n_eval < 1 || n_eval > BOSOT_MAX_EVAL) { std::snprintf(msg, sizeof(msg), "%s: bad sizes", who); return set_error(BOSOT_EINVAL, msg); }
@@ -216,9 +225,9 @@ static int acquire_on_device(const char* who, const uint8_t* d_trees, int64_t n_
   if (n_cand == 0 && d_n_bad) return cuda_check(cudaMemsetAsync(d_n_bad, 0, sizeof(int32_t), st), "cudaMemsetAsync");
   // one set of launches: cutting a device-resident pool into chunks on two streams was measured slower (4.07 vs 3.95 ms)
   if (int rc = launch_pairs(d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale, K, nullptr,
-                            nullptr, W.ld, status, w + W.off_recs, pairs_scratch_bytes(n_cand), st, d_n_bad, true)) return rc;
+                            nullptr, W.ld, status, w + W.off_recs, pairs_scratch_bytes(n_cand), st, d_n_bad, true, f32)) return rc;
   return launch_posterior(K, n_cand, W.ld, n_eval, d_Linv, ldl, d_beta, mean_c, variance, acq_kind, d_current_max, xi,
-                          ucb_beta, d_mu, d_sigma, d_acq, st, d_peers, n_peers, peer_off);
+                          ucb_beta, d_mu, d_sigma, d_acq, st, d_peers, n_peers, peer_off, f32);
 }
 }  // namespace bosot
 
@@ -232,6 +241,21 @@ extern "C" int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, cons
   return acquire_on_device("bosot_acquire_device", d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale,
                            d_Linv, ldl, d_beta, mean_c, acq_kind, d_current_max, xi, ucb_beta, d_work, work_bytes,
                            d_mu, d_sigma, d_acq, d_n_bad, nullptr, 0, 0, (cudaStream_t)stream);
+}
+
+// fp32 variant: the Gram panel in the work buffer and the three outputs are float arrays; the evaluated-set side
+// (L^-1, beta, current_max) and the accumulation of the posterior stay fp64
+extern "C" int bosot_acquire_device_f32(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,
+                                        const void* d_eval_blob, int n_eval, const double weights[3],
+                                        double variance, double lengthscale,
+                                        const double* d_Linv, int ldl, const double* d_beta, double mean_c,
+                                        int acq_kind, const double* d_current_max, double xi, double ucb_beta,
+                                        void* d_work, size_t work_bytes,
+                                        float* d_mu, float* d_sigma, float* d_acq, int32_t* d_n_bad, void* stream) {
+  return acquire_on_device("bosot_acquire_device_f32", d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale,
+                           d_Linv, ldl, d_beta, mean_c, acq_kind, d_current_max, xi, ucb_beta, d_work, work_bytes,
+                           reinterpret_cast<double*>(d_mu), reinterpret_cast<double*>(d_sigma), reinterpret_cast<double*>(d_acq),
+                           d_n_bad, nullptr, 0, 0, (cudaStream_t)stream, true);
 }
 
 extern "C" int bosot_acquire_device_scatter(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,

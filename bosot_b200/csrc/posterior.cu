@@ -68,6 +68,9 @@ __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, doub
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// KT = double, or float for the fp32 entry points: K*, mu, sigma and acq are then float arrays (PostParams keeps
+// them as double pointers), the tile is widened to fp64 while it is staged and everything else is unchanged.
+template <typename KT>
 __global__ void __launch_bounds__(kPostThreads, 2)
 posterior_kernel(PostParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -91,7 +94,7 @@ posterior_kernel(PostParams p) {
     // stage the K* tile (rows = candidates); rows beyond the tile and columns >= E are zero
     for (int x = threadIdx.x; x < kPostCand * tld; x += kPostThreads) {
       const int c = x / tld, j = x - c * tld;
-      Ks[x] = (c < in_tile && j < E) ? __ldg(&p.Kstar[(c0 + c) * p.ld + j]) : 0.0;
+      Ks[x] = (c < in_tile && j < E) ? (double)__ldg(reinterpret_cast<const KT*>(p.Kstar) + (c0 + c) * p.ld + j) : 0.0;
     }
     __syncthreads();
 
@@ -166,8 +169,8 @@ posterior_kernel(PostParams p) {
       const double var = p.variance - ss;
       const double sg = sqrt(var);
       const double mval = mus[c];
-      if (p.mu) p.mu[c0 + c] = mval;
-      if (p.sigma) p.sigma[c0 + c] = sg;
+      if (p.mu) reinterpret_cast<KT*>(p.mu)[c0 + c] = (KT)mval;
+      if (p.sigma) reinterpret_cast<KT*>(p.sigma)[c0 + c] = (KT)sg;
       if (p.acq) {
         double a;
         if (p.acq_kind == BOSOT_ACQ_EI) {
@@ -179,7 +182,7 @@ posterior_kernel(PostParams p) {
         } else {
           a = mval;
         }
-        p.acq[c0 + c] = a;
+        reinterpret_cast<KT*>(p.acq)[c0 + c] = (KT)a;
         if (p.peers) {
 #pragma unroll 1
           for (int r = 0; r < p.n_peers; ++r) p.peers[r][p.peer_off + c0 + c] = a;
@@ -599,12 +602,13 @@ __global__ void fp64_mixed_probe_kernel(double* out, int iters) {
 int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_eval, const double* d_Linv, int ldl,
                      const double* d_beta, double mean_c, double variance, int acq_kind, const double* d_current_max,
                      double xi, double ucb_beta, double* d_mu, double* d_sigma, double* d_acq, cudaStream_t stream,
-                     double* const* d_peers, int n_peers, int64_t peer_off) {
+                     double* const* d_peers, int n_peers, int64_t peer_off, bool f32) {
   if (!d_Kstar || !d_Linv || !d_beta || n_cand < 0) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: null argument");
   if (n_eval < 1 || n_eval > BOSOT_MAX_EVAL || ld < n_eval) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: bad n_eval / ld");
   if (ldl < n_eval || (ldl % kRowBlk) != 0)
     return set_error(BOSOT_EINVAL, "bosot_posterior_acq: Linv must be [ldl][ldl] with ldl a multiple of 16 and >= n_eval");
   if (acq_kind == BOSOT_ACQ_EI && d_acq && !d_current_max) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: EI needs current_max");
+  if (f32 && d_peers) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: the peer scatter is fp64 only");
   if (d_peers && (!d_acq || n_peers < 1 || n_peers > 64 || peer_off < 0))
     return set_error(BOSOT_EINVAL, "bosot_posterior_acq: the peer scatter needs d_acq, 1 <= n_peers <= 64 and a non-negative offset");
   if (n_cand == 0) return BOSOT_OK;
@@ -623,7 +627,7 @@ int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_ev
   const bool early = n_cand <= 32768;  // programmatic dependent launch only where launch latency matters (see launch_pairs)
 
   // warp-specialised TMA variant: needs 16-byte aligned rows of whole 16-byte units
-  const bool tma_ok = (ld % 2 == 0) && (n_eval % 2 == 0 || ld > n_eval) && !(reinterpret_cast<uintptr_t>(d_Kstar) & 15);
+  const bool tma_ok = !f32 && (ld % 2 == 0) && (n_eval % 2 == 0 || ld > n_eval) && !(reinterpret_cast<uintptr_t>(d_Kstar) & 15);
   if (tma_ok) {
     static std::atomic<bool> ws_attr[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
     if (!(dev < 64 && ws_attr[dev])) {
@@ -663,18 +667,21 @@ int launch_posterior(const double* d_Kstar, int64_t n_cand, int64_t ld, int n_ev
   if (smem > smem_cap) return set_error(BOSOT_EINVAL, "bosot_posterior_acq: n_eval too large for shared memory");
   static std::atomic<bool> attr_set[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
   if (!(dev < 64 && attr_set[dev])) {
-    if (int rc = cuda_check(cudaFuncSetAttribute(posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
+    if (int rc = cuda_check(cudaFuncSetAttribute(posterior_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
+                            "cudaFuncSetAttribute(posterior_kernel)")) return rc;
+    if (int rc = cuda_check(cudaFuncSetAttribute(posterior_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
                             "cudaFuncSetAttribute(posterior_kernel)")) return rc;
     if (dev < 64) attr_set[dev] = true;
   }
+  void (*generic)(PostParams) = f32 ? posterior_kernel<float> : posterior_kernel<double>;
   int per_sm = 1;
-  if (int rc = cuda_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, posterior_kernel, kPostThreads, smem),
+  if (int rc = cuda_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, generic, kPostThreads, smem),
                           "cudaOccupancyMaxActiveBlocksPerMultiprocessor")) return rc;
   if (per_sm < 1) per_sm = 1;
   const int64_t tiles = (n_cand + kPostCand - 1) / kPostCand;
   const int64_t wave = (int64_t)sms * per_sm;
   const int64_t grid = tiles < wave ? tiles : wave;
-  if (int rc = cuda_check(launch_pdl(early, posterior_kernel, dim3((unsigned)grid), dim3(kPostThreads), smem, stream, p), "cudaLaunchKernelEx(posterior_kernel)")) return rc;
+  if (int rc = cuda_check(launch_pdl(early, generic, dim3((unsigned)grid), dim3(kPostThreads), smem, stream, p), "cudaLaunchKernelEx(posterior_kernel)")) return rc;
   return after_launch("posterior_kernel");
 }
 

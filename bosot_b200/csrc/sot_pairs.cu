@@ -30,6 +30,7 @@
 //                                      The next tree's record is prefetched into registers while the
 //                                      current one is processed.
 #include <atomic>
+#include <type_traits>
 #include "sot_common.cuh"
 #include "launch.cuh"
 #include "fast_math.cuh"
@@ -481,10 +482,19 @@ __device__ __forceinline__ double u32_to_f64(uint32_t m) {
 }
 
 // R: evaluated trees per lane per tile; kExtra: also write D and/or Df; kFused: no scan launch in front, every warp scans
-// its candidate itself (warp_scan_tree) straight from the flat records; kFast: bounded Gram argument (exp_table_group)
-template <int R, bool kExtra, bool kFused, bool kFast>
+// its candidate itself (warp_scan_tree) straight from the flat records; kMode: 0 = general exp_nonpos route, 1 = bounded
+// Gram argument (exp_table_group), 2 = fp32 outputs (K / D / Df point to float arrays of the same shape: the integer
+// minima and the distances are formed as in the fp64 modes, the Gram entry is variance * ex2.approx in fp32)
+template <typename T>
+__device__ __forceinline__ void store_out(double* base, size_t idx, double v) {
+  reinterpret_cast<T*>(base)[idx] = (T)v;
+}
+
+template <int R, bool kExtra, bool kFused, int kMode>
 __global__ void __launch_bounds__(kMaxPairWarps * 32, 1)
 sot_pair_kernel(PairParams p, bosot_grammar g) {
+  constexpr bool kFast = kMode == 1, kF32 = kMode == 2;
+  using OutT = typename std::conditional<kF32, float, double>::type;
   constexpr int RP = (R + 1) / 2;  // packed pairs of evaluated trees per lane
   extern __shared__ __align__(16) uint8_t smem[];
   const int lane = threadIdx.x & 31;
@@ -626,10 +636,10 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
 #pragma unroll 1
       for (int e = lane; e < ld_i; e += 32) {  // padding columns stay finite like those of every other row
         const double v = e < E ? qnan : 0.0;
-        if (p.K) p.K[row + e] = v;
+        if (p.K) store_out<OutT>(p.K, row + e, v);
         if (e < E) {
-          if (p.D) p.D[row + e] = v;
-          if (p.Df) { p.Df[row + e] = v; p.Df[plane + row + e] = v; p.Df[2 * plane + row + e] = v; }
+          if (p.D) store_out<OutT>(p.D, row + e, v);
+          if (p.Df) { store_out<OutT>(p.Df, row + e, v); store_out<OutT>(p.Df, plane + row + e, v); store_out<OutT>(p.Df, 2 * plane + row + e, v); }
         }
       }
       if (lane == 0 && p.bad) atomicAdd(p.bad, 1);
@@ -824,27 +834,41 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
             // when the histograms coincide (like the reference), and (1/Ta)(1/Tb) first keeps D(a,b) == D(b,a) bitwise
             const double d_sub = u32_to_f64((uint32_t)nn * tb_sub - m_sub) * (rTa2_sub * rsp[32 * r]);
             const double d_path = u32_to_f64((uint32_t)nl * tb_path - m_path) * (rTa2_path * rpp[32 * r]);
-            if (kExtra || !kFast) {
+            if (kExtra || kMode == 0) {
               // sum_f w_f * D_f in feature_type_list order (kernel_kernel_grammar_tree.py:159-161)
               const double d = __dadd_rn(__dadd_rn(__dmul_rn(p.w_dim, ddim[r]), __dmul_rn(p.w_path, d_path)),
                                          __dmul_rn(p.w_sub, d_sub));
               if (kExtra) {
                 const int e = eb + 32 * r;
                 if (e < E) {
-                  if (p.Df) { p.Df[row + e] = ddim[r]; p.Df[plane + row + e] = d_path; p.Df[2 * plane + row + e] = d_sub; }
-                  if (p.D) p.D[row + e] = d;
+                  if (p.Df) { store_out<OutT>(p.Df, row + e, ddim[r]); store_out<OutT>(p.Df, plane + row + e, d_path); store_out<OutT>(p.Df, 2 * plane + row + e, d_sub); }
+                  if (p.D) store_out<OutT>(p.D, row + e, d);
                 }
               }
               x[i] = d * p.neg_inv_lsq;
             }
             // bounded hyper-parameters: the Gram argument -d / l^2 as one fused sum of the three terms (same value for
             // (a, b) and (b, a), exactly -0 for coinciding histograms)
-            if (kFast) x[i] = fma(p.a_sub, d_sub, fma(p.a_path, d_path, p.a_dim * ddim[r]));
+            if (kMode != 0) x[i] = fma(p.a_sub, d_sub, fma(p.a_path, d_path, p.a_dim * ddim[r]));
           } else {
             x[i] = 0.0;
           }
         }
-        if (p.K) {
+        if (p.K && kF32) {
+          // fp32 mode: one conversion, ex2.approx on the special-function unit (2 ulp of fp32), 4-byte stores
+          const float varf = (float)p.variance;
+#pragma unroll
+          for (int i = 0; i < kG; ++i) {
+            const int r = r0 + i, e = eb + 32 * r;
+            if (r < R) {
+              const float kv = varf * __expf((float)x[i]);
+              float* Kf = reinterpret_cast<float*>(p.K);
+              if (R < kMaxR && r < R - 1) Kf[row + e] = kv;
+              else if (e < ld_i) Kf[row + e] = e < E ? kv : 0.0f;
+            }
+          }
+        }
+        if (p.K && !kF32) {
           if (kFast) exp_table_group<kG>(x, exp_tab);  // variance included
           else exp_nonpos_group<kG>(x);
 #pragma unroll
@@ -874,7 +898,7 @@ size_t pairs_scratch_bytes(int64_t n_cand) { return align16(kScratchHead + (size
 int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar, const void* d_eval_blob,
                  int n_eval, const double weights[3], double variance, double lengthscale, double* d_K, double* d_D,
                  double* d_Df, int64_t ld, int32_t* d_status, void* d_scratch, size_t scratch_bytes, cudaStream_t stream,
-                 int32_t* d_bad, bool zero_bad) {
+                 int32_t* d_bad, bool zero_bad, bool f32) {
   if (!grammar || !d_eval_blob || !weights || n_cand < 0 || (n_cand > 0 && (!d_trees || !d_scratch)))
     return set_error(BOSOT_EINVAL, "bosot_sot_pairs: null argument");
   if (n_eval < 1 || n_eval > BOSOT_MAX_EVAL) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: n_eval out of range");
@@ -903,7 +927,7 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   // (negative or non-finite weights, extreme length scales) takes the general exp_nonpos route.
   const double x_min = 2.0 * (grammar->n_blocks * p.w_dim + p.w_path + p.w_sub) * p.neg_inv_lsq;
   const bool fast = p.w_dim >= 0.0 && p.w_path >= 0.0 && p.w_sub >= 0.0 && x_min >= -600.0 && x_min <= 0.0 &&
-                    variance >= 0x1p-100 && variance <= 0x1p100 && !(experiment_flag() & 4);
+                    variance >= 0x1p-100 && variance <= 0x1p100 && !(experiment_flag() & 4) && !f32;
   p.K = d_K;
   p.D = d_D;
   p.Df = d_Df;
@@ -957,18 +981,18 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   const int rounds = (n_eval + 31) / 32;  // evaluated trees per lane; beyond 256 trees: tiles of 256 (e_pad is a multiple of 256)
   const int R = rounds < kMaxR ? rounds : kMaxR;
   using KernelFn = void (*)(PairParams, bosot_grammar);
-#define BOSOT_PAIR_X(r, x, f) {sot_pair_kernel<r, x, f, false>, sot_pair_kernel<r, x, f, true>}
+#define BOSOT_PAIR_X(r, x, f) {sot_pair_kernel<r, x, f, 0>, sot_pair_kernel<r, x, f, 1>, sot_pair_kernel<r, x, f, 2>}
 #define BOSOT_PAIR_ROW(r) {{BOSOT_PAIR_X(r, false, false), BOSOT_PAIR_X(r, false, true)}, {BOSOT_PAIR_X(r, true, false), BOSOT_PAIR_X(r, true, true)}}
-  static const KernelFn table[kMaxR][2][2][2] = {BOSOT_PAIR_ROW(1), BOSOT_PAIR_ROW(2), BOSOT_PAIR_ROW(3), BOSOT_PAIR_ROW(4),
+  static const KernelFn table[kMaxR][2][2][3] = {BOSOT_PAIR_ROW(1), BOSOT_PAIR_ROW(2), BOSOT_PAIR_ROW(3), BOSOT_PAIR_ROW(4),
                                                  BOSOT_PAIR_ROW(5), BOSOT_PAIR_ROW(6), BOSOT_PAIR_ROW(7), BOSOT_PAIR_ROW(8)};
 #undef BOSOT_PAIR_ROW
 #undef BOSOT_PAIR_X
-  KernelFn kernel = table[R - 1][extra ? 1 : 0][fused ? 1 : 0][fast ? 1 : 0];
+  KernelFn kernel = table[R - 1][extra ? 1 : 0][fused ? 1 : 0][f32 ? 2 : (fast ? 1 : 0)];
   static std::atomic<bool> attr_set[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
   if (!(dev < 64 && attr_set[dev])) {
     for (int r = 0; r < kMaxR; ++r)
-      for (int x = 0; x < 8; ++x)
-        if (int rc = cuda_check(cudaFuncSetAttribute(table[r][x >> 2][(x >> 1) & 1][x & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
+      for (int x = 0; x < 12; ++x)
+        if (int rc = cuda_check(cudaFuncSetAttribute(table[r][x / 6][(x / 3) & 1][x % 3], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap),
                                 "cudaFuncSetAttribute(sot_pair_kernel)")) return rc;
     if (dev < 64) attr_set[dev] = true;
   }
@@ -996,5 +1020,15 @@ extern "C" int bosot_sot_pairs(const uint8_t* d_trees, int64_t n_cand, const bos
                                double* d_K, double* d_D, double* d_Df, int64_t ld,
                                int32_t* d_status, void* d_scratch, size_t scratch_bytes, void* stream) {
   return bosot::launch_pairs(d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale, d_K, d_D,
-                             d_Df, ld, d_status, d_scratch, scratch_bytes, (cudaStream_t)stream, nullptr, false);
+                             d_Df, ld, d_status, d_scratch, scratch_bytes, (cudaStream_t)stream, nullptr, false, false);
+}
+
+extern "C" int bosot_sot_pairs_f32(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,
+                                   const void* d_eval_blob, int n_eval, const double weights[3],
+                                   double variance, double lengthscale,
+                                   float* d_K, float* d_D, float* d_Df, int64_t ld,
+                                   int32_t* d_status, void* d_scratch, size_t scratch_bytes, void* stream) {
+  return bosot::launch_pairs(d_trees, n_cand, grammar, d_eval_blob, n_eval, weights, variance, lengthscale,
+                             reinterpret_cast<double*>(d_K), reinterpret_cast<double*>(d_D), reinterpret_cast<double*>(d_Df), ld,
+                             d_status, d_scratch, scratch_bytes, (cudaStream_t)stream, nullptr, false, true);
 }

@@ -160,25 +160,30 @@ def sot_pairs(
     lengthscale: float,
     want: Sequence[str] = ("K",),
     check: bool = True,
+    dtype: torch.dtype = torch.float64,
 ) -> Dict[str, torch.Tensor]:
     """SOT distances / Gram between candidate trees (rows) and the evaluated set (columns).
 
     ``weights`` = (w_DIM_WISE, w_PATHS, w_SUBTREES) = alpha_f / sum(alpha)
-    (kernel_kernel_grammar_tree.py:159-161).  ``want`` subset of {"K", "D", "Df"}."""
+    (kernel_kernel_grammar_tree.py:159-161).  ``want`` subset of {"K", "D", "Df"}.
+    ``dtype=torch.float32``: the reduced-precision variant (C-ABI ``bosot_sot_pairs_f32``)."""
     _need_cuda(trees, "candidate trees")
+    if dtype not in (torch.float64, torch.float32):
+        raise ValueError("sot_pairs: dtype must be torch.float64 or torch.float32")
     lib = _lib.load()
     n, E, dev = trees.shape[0], state.n_eval, trees.device
     out = {}
     if "K" in want:
-        out["K"] = torch.empty((n, E), dtype=torch.float64, device=dev)
+        out["K"] = torch.empty((n, E), dtype=dtype, device=dev)
     if "D" in want:
-        out["D"] = torch.empty((n, E), dtype=torch.float64, device=dev)
+        out["D"] = torch.empty((n, E), dtype=dtype, device=dev)
     if "Df" in want:
-        out["Df"] = torch.empty((3, n, E), dtype=torch.float64, device=dev)
+        out["Df"] = torch.empty((3, n, E), dtype=dtype, device=dev)
     status = torch.empty(n, dtype=torch.int32, device=dev)
     scratch = torch.empty(max(16, lib.bosot_sot_pairs_scratch_bytes(n)), dtype=torch.uint8, device=dev)
+    entry = lib.bosot_sot_pairs if dtype == torch.float64 else lib.bosot_sot_pairs_f32
     with torch.cuda.device(dev):
-        rc = lib.bosot_sot_pairs(
+        rc = entry(
             trees.data_ptr(), n, C.byref(state.grammar.c_struct), state.blob.data_ptr(), E, _DBL3(*[float(w) for w in weights]),
             float(variance), float(lengthscale), _ptr(out.get("K")), _ptr(out.get("D")), _ptr(out.get("Df")), E,
             status.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream(dev),
@@ -222,16 +227,20 @@ def posterior_acq(
     xi: float = 0.01,
     ucb_beta: float = 3.0,
 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """(mu, sigma, acq) for every row of K* (C-ABI ``bosot_posterior_acq``)."""
+    """(mu, sigma, acq) for every row of K* (C-ABI ``bosot_posterior_acq``; a float32 K* takes
+    ``bosot_posterior_acq_f32`` and returns float32 tensors)."""
     _need_cuda(Kstar, "K*")
+    if Kstar.dtype not in (torch.float64, torch.float32):
+        raise ValueError("posterior_acq: K* must be float64 or float32")
     lib = _lib.load()
     n, E = Kstar.shape
     dev = Kstar.device
-    mu = torch.empty(n, dtype=torch.float64, device=dev)
-    sigma = torch.empty(n, dtype=torch.float64, device=dev)
-    acq = torch.empty(n, dtype=torch.float64, device=dev)
+    mu = torch.empty(n, dtype=Kstar.dtype, device=dev)
+    sigma = torch.empty(n, dtype=Kstar.dtype, device=dev)
+    acq = torch.empty(n, dtype=Kstar.dtype, device=dev)
+    entry = lib.bosot_posterior_acq if Kstar.dtype == torch.float64 else lib.bosot_posterior_acq_f32
     with torch.cuda.device(dev):
-        rc = lib.bosot_posterior_acq(
+        rc = entry(
             Kstar.data_ptr(), n, Kstar.stride(0), E, Linv.data_ptr(), Linv.shape[1], beta.data_ptr(), float(mean_c), float(variance),
             int(acq_kind), _ptr(current_max), float(xi), float(ucb_beta), mu.data_ptr(), sigma.data_ptr(), acq.data_ptr(), _stream(dev),
         )
@@ -341,8 +350,11 @@ class AcquisitionEngine:
         return self._work
 
     def acquire_device(self, trees: torch.Tensor, out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None,
-                       scatter: Optional[Tuple[int, int, int]] = None):
+                       scatter: Optional[Tuple[int, int, int]] = None, dtype: torch.dtype = torch.float64):
         """Candidates already resident in HBM -> (mu, sigma, acq) device tensors.
+
+        ``dtype=torch.float32`` selects the reduced-precision variant (C-ABI ``bosot_acquire_device_f32``: fp32 Gram
+        panel and fp32 outputs, fp64 accumulation; 1e-4 relative against the fp64 path).  Never the default.
 
         ``scatter = (peer_ptrs_dev, n_peers, row_offset)``: the posterior kernel additionally stores every acquisition
         value into the peer-mapped result vectors of all GPUs of the node at ``row_offset + i`` (C-ABI
@@ -352,9 +364,15 @@ class AcquisitionEngine:
         ``bad_tree_count()`` (synchronises) or ``raise_on_bad_trees()`` after the results have been read."""
         _need_cuda(trees, "candidate trees")
         n = trees.shape[0]
+        if dtype not in (torch.float64, torch.float32):
+            raise ValueError("acquire_device: dtype must be torch.float64 or torch.float32")
         if out is None:
-            out = tuple(torch.empty(n, dtype=torch.float64, device=self.device) for _ in range(3))
+            out = tuple(torch.empty(n, dtype=dtype, device=self.device) for _ in range(3))
         mu, sigma, acq = out
+        if any(t.dtype != dtype for t in out):
+            raise ValueError("acquire_device: output tensors must have dtype %s" % dtype)
+        if dtype == torch.float32 and scatter is not None:
+            raise ValueError("acquire_device: the peer scatter is fp64 only")
         w = self._workspace(n)
         lib = _lib.load()
         head = (trees.data_ptr(), n, C.byref(self.grammar.c_struct), self.state.blob.data_ptr(), self.n_eval, self._wdbl,
@@ -362,7 +380,9 @@ class AcquisitionEngine:
                 self.acq_kind, self.current_max.data_ptr(), self.xi, self.ucb_beta, w.data_ptr(), w.numel(),
                 mu.data_ptr(), sigma.data_ptr(), acq.data_ptr(), self._bad.data_ptr())
         with torch.cuda.device(self.device):
-            if scatter is None:
+            if dtype == torch.float32:
+                rc = lib.bosot_acquire_device_f32(*head, _stream(self.device))
+            elif scatter is None:
                 rc = lib.bosot_acquire_device(*head, _stream(self.device))
             else:
                 ptrs, n_peers, offset = scatter

@@ -45,7 +45,7 @@
  * device, guarded by a per-device mutex that is held only while work is ENQUEUED, released by
  * bosot_shutdown()).
  * fp64 throughout ("f64" path); the reference computes in float64 as well
- * (kernel_kernel_grammar_tree.py:35).
+ * (kernel_kernel_grammar_tree.py:35).  The *_f32 entry points are the optional reduced-precision variants.
  */
 #ifndef BOSOT_B200_H
 #define BOSOT_B200_H
@@ -228,6 +228,35 @@ int bosot_acquire_device(const uint8_t* d_trees, int64_t n_cand, const bosot_gra
                          int acq_kind, const double* d_current_max, double xi, double ucb_beta,
                          void* d_work, size_t work_bytes,
                          double* d_mu, double* d_sigma, double* d_acq, int32_t* d_n_bad, void* stream);
+
+/* ---- fp32 variants (SURVEY.md 8b "fp32 variants", 8d "fp32 mode: replace 8 by 4") -------------------------
+ * Same contracts with float arrays for everything that scales with the number of candidates: the Gram / distance
+ * outputs of the pair kernel (K, D, Df: [n_cand][ld] floats), K* read by the posterior, and mu / sigma / acq.
+ * The integer minima and the per-feature distances are formed exactly as in the fp64 entry points and rounded once;
+ * the Gram entry is variance * exp(x) with the hardware ex2 approximation (2 ulp of fp32).  Everything that belongs
+ * to the evaluated set (LinvF, beta, current_max, the hyper-parameters) and the accumulation of the posterior stay
+ * fp64: sigma^2 = variance - ||L^-1 k*||^2 cancels, and a condition number of 1e5 times fp32 rounding would not meet
+ * any tolerance.  Stated bar (tests/test_gpu_f32.py): 1e-4 relative on D, K, mu, sigma and EI against the fp64 oracle
+ * (sigma and EI: plus 1e-4 * sqrt(variance) absolute, the share of the fp32 rounding of K* that L^-1 amplifies).
+ * The reference itself computes in float64 (kernels/kernel_kernel_grammar_tree.py:35); these entry points trade
+ * accuracy for half the Gram bytes and are never the default of the Python layer. */
+int bosot_sot_pairs_f32(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,
+                        const void* d_eval_blob, int n_eval, const double weights[3],
+                        double variance, double lengthscale,
+                        float* d_K, float* d_D, float* d_Df, int64_t ld,
+                        int32_t* d_status, void* d_scratch, size_t scratch_bytes, void* stream);
+int bosot_posterior_acq_f32(const float* d_Kstar, int64_t n_cand, int64_t ld, int n_eval,
+                            const double* d_LinvF, int ldl, const double* d_beta, double mean_c, double variance,
+                            int acq_kind, const double* d_current_max, double xi, double ucb_beta,
+                            float* d_mu, float* d_sigma, float* d_acq, void* stream);
+/* d_work: bosot_acquire_work_bytes(n_cand, n_eval) bytes as for the fp64 call (the Gram panel uses half of its share) */
+int bosot_acquire_device_f32(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* grammar,
+                             const void* d_eval_blob, int n_eval, const double weights[3],
+                             double variance, double lengthscale,
+                             const double* d_LinvF, int ldl, const double* d_beta, double mean_c,
+                             int acq_kind, const double* d_current_max, double xi, double ucb_beta,
+                             void* d_work, size_t work_bytes,
+                             float* d_mu, float* d_sigma, float* d_acq, int32_t* d_n_bad, void* stream);
 
 /* ---- row-sharded pools: posterior + acquisition fused with the exchange of the result ----
  * The reference has no multi-process path; here the candidate pool is split into row blocks over the GPUs of one

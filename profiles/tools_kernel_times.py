@@ -76,4 +76,15 @@ print("pairs  ms median %.4f min %.4f" % timed(k_pairs))
 print("post   ms median %.4f min %.4f" % timed(k_post))
 print("device ms median %.4f min %.4f" % timed(lambda: eng.acquire_device(ca, out=(mu, sg, ei))))
 print("e2e    ms median %.4f min %.4f" % timed(k_e2e))
+if os.environ.get("BOSOT_TIME_F32"):  # the optional fp32 entry points (bosot_sot_pairs_f32 / bosot_acquire_device_f32)
+    K32 = torch.empty((pool, n_eval), dtype=torch.float32, device=dev)
+    o32 = tuple(torch.empty(pool, dtype=torch.float32, device=dev) for _ in range(3))
+
+    def k_pairs32():
+        _lib.check(lib.bosot_sot_pairs_f32(ca.data_ptr(), pool, C.byref(gram.c_struct), eng.state.blob.data_ptr(), n_eval, wd, 1.3, 0.8,
+                                           K32.data_ptr(), None, None, n_eval, status.data_ptr(), scratch.data_ptr(), scratch.numel(), st))
+
+    print("pairs32  ms median %.4f min %.4f" % timed(k_pairs32))
+    print("device32 ms median %.4f min %.4f" % timed(lambda: eng.acquire_device(ca, out=o32, dtype=torch.float32)))
+    print("check32  max |ei32 - ei| %.3e" % float((o32[2].double() - ei).abs().max()))
 print("check  ei sum %.12e  sigma nan %d" % (float(ei.sum()), int(torch.isnan(sg).sum())))
