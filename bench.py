@@ -408,6 +408,34 @@ def main() -> None:
                   engine_build_ms=build_50, e2e_with_update_ms=ms4_e2e + build_50["cuda_event_ms"],
                   call_100_x_50_device_ms=ms100)
 
+    # Optional fp32 entry points (SURVEY 8b / north_star "1e-4 in fp32") on the headline workload: a separate line with
+    # dtype "f32", never the headline.  Gram panel and outputs in fp32, fp64 accumulation in the posterior.
+    f32 = {}
+    if rank == 0 and world == 1:
+        K32 = torch.empty((n_local, N_EVAL), dtype=torch.float32, device=dev)
+        o32 = tuple(torch.empty(n_local, dtype=torch.float32, device=dev) for _ in range(3))
+
+        def k_pairs32():
+            _lib.check(lib.bosot_sot_pairs_f32(d_ca.data_ptr(), n_local, C.byref(gram.c_struct), eng.state.blob.data_ptr(), N_EVAL, wd,
+                                               hyp.variance, hyp.lengthscale, K32.data_ptr(), None, None, N_EVAL, status.data_ptr(),
+                                               scratch.data_ptr(), scratch.numel(), stream))
+
+        ms_p32 = timed(k_pairs32, args.steps, 3, collective=False)
+        ms_d32 = timed(lambda: eng.acquire_device(d_ca, out=o32, dtype=torch.float32), args.steps, 3, collective=False)
+        ref64 = eng.acquire_device(d_ca)
+        dev32 = [float(((a.double() - b).abs() / (1e-4 * b.abs() + 1e-4 * hyp.variance ** 0.5)).max()) for a, b in zip(o32, ref64)]
+        alg32 = (4.0 + 64.0 / N_EVAL + 64.0 / n_local) * n_local * N_EVAL
+        f32 = dict(dtype="f32", workload="c5_stress_1M_x_200", pair_launch_ms=ms_p32, ms_per_step=ms_d32,
+                   pairs_per_s=n_local * N_EVAL / (ms_d32 * 1e-3), ei_candidates_per_s=n_local / (ms_d32 * 1e-3),
+                   roofline=dict(bound="hbm", kernel="sot_pair_kernel (fp32 outputs)", achieved=alg32 / (ms_p32 * 1e-3) / 1e9,
+                                 peak=measured_peaks()["hbm_gbs"], unit="GB/s", frac=alg32 / (ms_p32 * 1e-3) / 1e9 / measured_peaks()["hbm_gbs"],
+                                 algorithmic_bytes_per_launch=alg32),
+                   share_of_stated_tolerance_used=dict(mu=dev32[0], sigma=dev32[1], ei=dev32[2],
+                                                       scale="max |x32 - x64| / (1e-4 |x64| + 1e-4 sqrt(variance)) over the pool; must stay below 1"),
+                   note="the fp32 posterior widens K* to fp64 while staging its tiles (generic kernel, no TMA ring): slower than the fp64 step; "
+                        "the pair launch is what fp32 speeds up")
+        del K32, o32, ref64
+
     # One BO loop at the shape of BASELINE.json config 4 (Airfoil-shaped: CKSHighDim d = 5, 10k-candidate EA pool per step)
     # through the reference-facing API: model update (ML-II fit on the device) + EA acquisition optimisation per BO step;
     # a deterministic structural objective stands in for the reference's model-evidence oracle (out of scope).
@@ -597,6 +625,7 @@ def main() -> None:
             cpu_baseline=cpu,
             c4_10k_x_50=c4,
             hellinger_10k_x_50=hell,
+            f32=f32,
             bo_loop_c4=bo_loop,
         )
         print(json.dumps(line), flush=True)
