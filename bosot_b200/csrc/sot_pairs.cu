@@ -42,6 +42,11 @@ int experiment_flag();
 
 constexpr int kMaxPairWarps = 28;   // one persistent CTA of up to 28 warps per SM (72 registers per thread; measured: 20 / 24 / 28 / 32 warps = 2.68 / 2.52 / 2.43 / 2.49 ms)
 constexpr int kScanThreads = 128;
+// Block-vector cache of the DIM_WISE distances (state mode, blocks of at most two kinds): the vector of a candidate in
+// one block of input dimensions is fixed by the leaf counts (c1, c2) of the block's kinds, so L1(block vector, state)
+// is tabulated once per CTA for all c1, c2 <= kBvMaxCount and a candidate only forms its index per block
+constexpr int kBvMaxCount = 5, kBvRadix = kBvMaxCount + 1, kBvEntries = kBvRadix * kBvRadix;
+constexpr int kBvStates = 20;  // states per cache row (the 200 x d = 5 benchmark set has 19 at most in a block)
 constexpr int kMaxR = 8;            // evaluated trees per lane per register tile (E <= 256 in one pass, else tiles of 256)
 constexpr int64_t kFusedScanMax = 16384;  // pools up to this size take the fused-scan path (no scan launch); measured
                                           // 10k x 50: 48 against 56 us per step, 100 x 50: 21 against 34 us, 30k x 80: 110 against 101 us (profiles/r2i_ab.log)
@@ -80,6 +85,7 @@ struct PairParams {
   int flags;                 // experiment switches (0 = product path)
   int32_t* status;           // fused-scan path only: per-tree defect codes (may be null)
   int n_symbols;
+  int bv_states;             // rows of the block-vector cache hold this many states (0 = no cache in this launch)
 };
 
 // per-warp shared memory: candidate dim-wise vector, block-state distance table, walk segments, accumulators, symbol counts
@@ -107,10 +113,10 @@ __host__ __device__ inline WarpLayout warp_layout(int e_pad, int n_dim_cols, int
 // The DIM_WISE section holds either the block-state tables (stateP + sid8T) or, when a block has more than
 // kMaxStates distinct vectors, the dense transposed matrix; it is sized for the larger of the two.
 struct StageLayout {
-  size_t off_meta, off_dim, off_sid, off_flat, off_rsub, off_rpath, off_symT2, off_nn2, off_nn, off_nl, off_exp, total;
+  size_t off_meta, off_dim, off_sid, off_flat, off_rsub, off_rpath, off_symT2, off_nn2, off_nn, off_nl, off_exp, off_bvw, off_bv, total;
   uint32_t b_meta, b_state, b_sid, b_flat, b_dimT, b_r, b_symT2, b_nn2, b_n, b_exp;
 };
-__host__ __device__ inline StageLayout stage_layout(int e_pad, int n_dim_cols, int n_symbols, int n_blocks, bool fast_exp) {
+__host__ __device__ inline StageLayout stage_layout(int e_pad, int n_dim_cols, int n_symbols, int n_blocks, bool fast_exp, int bv_states = 0) {
   StageLayout S;
   S.b_meta = (uint32_t)sizeof(DimMeta);
   S.b_state = (uint32_t)(sizeof(double) * (size_t)n_dim_cols * kMaxStates);
@@ -134,6 +140,8 @@ __host__ __device__ inline StageLayout stage_layout(int e_pad, int n_dim_cols, i
   o = align16(o);
   S.b_exp = fast_exp ? (uint32_t)(sizeof(double) * kExpTableSize) : 0u;
   S.off_exp = o;   o += S.b_exp;
+  S.off_bvw = o;   o += bv_states ? BOSOT_MAX_SYMBOLS : 0;                                          // index weight per symbol
+  S.off_bv = o;    o += sizeof(double) * (size_t)n_blocks * kBvEntries * bv_states;                 // [block][entry][state]
   S.total = align16(o);
   return S;
 }
@@ -509,7 +517,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   pdl_launch_dependents();  // a posterior launch behind this one may set up its shared memory early (it waits before reading K*)
   // ---- stage the evaluated set's dense tables once per (persistent) CTA: TMA bulk copies -> mbarrier
   // (the blob is the product of an OLDER launch than the scan in front of this one, so this may run before pdl_wait())
-  const StageLayout S = stage_layout(e_pad, g.n_dim_cols, g.n_symbols, g.n_blocks, kFast);
+  const StageLayout S = stage_layout(e_pad, g.n_dim_cols, g.n_symbols, g.n_blocks, kFast, p.bv_states);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
   if (threadIdx.x == 0) mbar_init(bar, 1);
   __syncthreads();
@@ -607,6 +615,63 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   const bool use_states = meta->use_states != 0;
   const int n_flat = meta->n_flat;
 
+  // ---- block-vector cache (see kBvMaxCount): usable when every block is NULL + at most two kinds, every counted symbol
+  // has its column, and no block has more states than a cache row holds; all threads reach the same verdict
+  const int bvS = p.bv_states;
+  const uint8_t* bvw = smem + S.off_bvw;
+  const uint8_t* bvc = smem + S.off_bv;
+  bool bv_on = bvS > 0 && use_states;
+  if (bv_on) {
+    int kinds_seen = 0, kinds_cols = 0;
+#pragma unroll 1
+    for (int b = 0; b < g.n_blocks; ++b) {
+      const int width = meta->bbeg[b + 1] - meta->bbeg[b];
+      bv_on = bv_on && width >= 1 && width <= 3 && meta->n_states[b] <= bvS;
+      kinds_cols += width - 1;
+    }
+#pragma unroll 1
+    for (int sy = 0; sy < g.n_symbols; ++sy) {
+      if (g.sym_block[sy] >= 0) {
+        bv_on = bv_on && meta->sym_pos[sy] >= 0;
+        ++kinds_seen;
+      }
+    }
+    bv_on = bv_on && kinds_seen == kinds_cols;
+    if (bv_on) {
+      uint8_t* w_out = smem + S.off_bvw;
+      double* c_out = reinterpret_cast<double*>(smem + S.off_bv);
+      for (int sy = threadIdx.x; sy < g.n_symbols; sy += blockDim.x) {
+        const int b = g.sym_block[sy];
+        int wgt = 0;
+        if (b >= 0) {
+          const int j = meta->sym_pos[sy];
+          const int rank = (j - meta->bbeg[b]) - (meta->null_pos[b] < j ? 1 : 0);
+          wgt = rank == 0 ? 1 : kBvRadix;
+        }
+        w_out[sy] = (uint8_t)wgt;
+      }
+      const int n_entries = g.n_blocks * kBvEntries * bvS;
+#pragma unroll 1
+      for (int x = threadIdx.x; x < n_entries; x += blockDim.x) {
+        const int st = x % bvS, en = (x / bvS) % kBvEntries, b = x / (bvS * kBvEntries);
+        if (st < meta->n_states[b]) {
+          const uint32_t c1 = en % kBvRadix, c2 = en / kBvRadix, tot = c1 + c2;
+          const int jn = meta->null_pos[b];
+          double sum = 0.0;  // the same values in the same order as the per-candidate table build below
+#pragma unroll 1
+          for (int j = meta->bbeg[b]; j < meta->bbeg[b + 1]; ++j) {
+            double a;
+            if (j == jn) a = tot == 0u ? 1.0 : 0.0;
+            else a = tot ? __ldg(&g_frac.v[(((j - meta->bbeg[b]) - (jn < j ? 1 : 0)) == 0 ? c1 : c2) * 33u + tot]) : 0.0;
+            sum += fabs(a - stateP[j * kMaxStates + st]);
+          }
+          c_out[x] = sum;
+        }
+      }
+    }
+    __syncthreads();  // bv_on is the same for every thread of the CTA
+  }
+
 #pragma unroll 1
   for (int e = 2 * lane; e < e_pad; e += 64) *reinterpret_cast<uint2*>(acc + e) = make_uint2(0u, 0u);
   auto claim = [&]() {
@@ -647,9 +712,11 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     }
 
     __syncwarp();  // acc[] is all zero here: zeroed before the loop, and every entry is cleared again by the epilogue that reads it
+    if (!bv_on) {
 #pragma unroll 1
-    for (int s = lane; s < g.n_symbols; s += 32) scnt[s] = 0u;  // only the grammar's symbols / blocks are ever read
-    if (lane < g.n_blocks) btot[lane] = 0u;
+      for (int s = lane; s < g.n_symbols; s += 32) scnt[s] = 0u;  // only the grammar's symbols / blocks are ever read
+    }
+    if (lane < g.n_blocks) btot[lane] = 0u;  // leaf count per block, or (cache) the index of the block's vector
     __syncwarp();
 
     // leaves: symbol multiplicities (SUBTREES leaf classes, DIM_WISE) and PATHS (key = symbol * 64 + code)
@@ -662,9 +729,22 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     const bool lead_pid = is_leaf && (__ffs(m_pid) - 1 == lane);
     const uint32_t cnt_sym = (uint32_t)__popc(m_sym);
     uint2 r_pid = make_uint2(0u, 0u);
-    if (lead_sym) {
+    const int blk = lead_sym ? (int)g.sym_block[sym] : -1;
+    bool cached = bv_on;  // DIM_WISE of this candidate through the block-vector cache
+    if (bv_on) {
+      if (blk >= 0) atomicAdd(&btot[blk], cnt_sym * bvw[sym]);
+      cached = !__any_sync(full, blk >= 0 && cnt_sym > (uint32_t)kBvMaxCount);
+      if (!cached) {  // a kind with more leaves than the cache covers: this candidate builds its own table
+        __syncwarp();
+#pragma unroll 1
+        for (int s = lane; s < g.n_symbols; s += 32) scnt[s] = 0u;
+        if (lane < g.n_blocks) btot[lane] = 0u;
+        __syncwarp();
+      }
+    }
+    if (!cached && lead_sym) {
       scnt[sym] = cnt_sym;
-      if (g.sym_block[sym] >= 0) atomicAdd(&btot[g.sym_block[sym]], cnt_sym);
+      if (blk >= 0) atomicAdd(&btot[blk], cnt_sym);
     }
     if (lead_pid) r_pid = __ldg(&range[hash_cap + BOSOT_MAX_SYMBOLS + pid]);
     const unsigned sym_leads = __ballot_sync(full, lead_sym);
@@ -687,15 +767,17 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
 
     // candidate DIM_WISE vector from the symbol counts (optimal_transport_mappings.py:88-108); count / total comes
     // from the table of correctly rounded quotients (== float(a) / float(b)); every permuted column is written
+    if (!cached) {
 #pragma unroll 1
-    for (int s = lane; s < g.n_symbols; s += 32) {
-      const int b = g.sym_block[s], j = meta->sym_pos[s];
-      if (b >= 0 && j >= 0) {
-        const uint32_t tot = btot[b];
-        avec[j] = tot ? __ldg(&g_frac.v[scnt[s] * 33u + tot]) : 0.0;
+      for (int s = lane; s < g.n_symbols; s += 32) {
+        const int b = g.sym_block[s], j = meta->sym_pos[s];
+        if (b >= 0 && j >= 0) {
+          const uint32_t tot = btot[b];
+          avec[j] = tot ? __ldg(&g_frac.v[scnt[s] * 33u + tot]) : 0.0;
+        }
       }
+      if (lane < g.n_blocks) avec[meta->null_pos[lane]] = btot[lane] == 0u ? 1.0 : 0.0;
     }
-    if (lane < g.n_blocks) avec[meta->null_pos[lane]] = btot[lane] == 0u ? 1.0 : 0.0;
 
     // Walk the postings of all matched features as ONE flattened list: an exclusive scan of the list lengths
     // over the lanes gives every feature its segment [start, start + len); the non-empty segments are compacted
@@ -740,7 +822,7 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
     walk(r_pid, (uint32_t)__popc(m_pid), (uint32_t)nl, 16);
 
     // block-state distance table: one (block, state) pair per lane and round
-    if (use_states) {
+    if (use_states && !cached) {
 #pragma unroll 1
       for (int k = lane; k < n_flat; k += 32) {
         const uint32_t dsc = flat[k];
@@ -789,9 +871,11 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
       // DIM_WISE: per block, then across blocks (the same grouping in both modes, so they agree bit for bit)
       if (use_states) {
         const uint8_t* sp = sid8T + eb;
-        const uint8_t* tb = reinterpret_cast<const uint8_t*>(tab);
 #pragma unroll 1
-        for (int b = 0; b < g.n_blocks; ++b, sp += e_pad, tb += 8 * kMaxStates) {
+        for (int b = 0; b < g.n_blocks; ++b, sp += e_pad) {
+          // row of L1(candidate block b, state): the cached row of the block's vector, or this candidate's own table
+          const uint8_t* tb = cached ? bvc + (size_t)((b * kBvEntries + (int)btot[b]) * bvS) * 8
+                                     : reinterpret_cast<const uint8_t*>(tab) + (size_t)b * 8 * kMaxStates;
 #pragma unroll
           for (int r = 0; r < R; ++r) ddim[r] += *reinterpret_cast<const double*>(tb + sp[32 * r]);
         }
@@ -967,7 +1051,7 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   // launch 2: pairs.  One persistent CTA per SM; small pools shrink the CTA so that every SM gets warps.
   int warps = kMaxPairWarps;
   while (warps > 1 && (n_cand + warps - 1) / warps < sms) warps >>= 1;
-  const StageLayout S = stage_layout(p.L.e_pad, grammar->n_dim_cols, grammar->n_symbols, grammar->n_blocks, fast);
+  StageLayout S = stage_layout(p.L.e_pad, grammar->n_dim_cols, grammar->n_symbols, grammar->n_blocks, fast);
   const size_t per_warp = warp_layout(p.L.e_pad, grammar->n_dim_cols, grammar->n_blocks, fused).total;
   const size_t smem_cap = 220 * 1024;
   size_t smem = S.total + (size_t)warps * per_warp;
@@ -976,6 +1060,18 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
     smem = S.total + (size_t)warps * per_warp;
   }
   if (smem > smem_cap) return set_error(BOSOT_EINVAL, "bosot_sot_pairs: n_eval too large for shared memory");
+  // Block-vector cache of the DIM_WISE distances: worth its set-up (a few thousand table entries per CTA) only for pools
+  // with hundreds of candidates per warp, and only when it fits beside the full set of warps.  Results are bit-identical
+  // with and without it (same values added in the same order), so the choice may depend on the pool size.
+  p.bv_states = 0;
+  if (!fused && !(experiment_flag() & 8)) {
+    const StageLayout Sbv = stage_layout(p.L.e_pad, grammar->n_dim_cols, grammar->n_symbols, grammar->n_blocks, fast, kBvStates);
+    if (Sbv.total + (size_t)warps * per_warp <= smem_cap) {
+      p.bv_states = kBvStates;
+      S = Sbv;
+      smem = S.total + (size_t)warps * per_warp;
+    }
+  }
 
   const bool extra = d_D != nullptr || d_Df != nullptr;
   const int rounds = (n_eval + 31) / 32;  // evaluated trees per lane; beyond 256 trees: tiles of 256 (e_pad is a multiple of 256)
