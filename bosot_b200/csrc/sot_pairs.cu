@@ -512,7 +512,9 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
   const int e_pad = p.L.e_pad;
   const int half_pad = e_pad >> 1;
   const unsigned full = 0xffffffffu;
-  const unsigned lt_mask = (1u << lane) - 1u, le_mask = (2u << lane) - 1u;
+  unsigned lt_mask, le_mask;  // special registers: one S2R where the compiler would rematerialise shift + subtract at every use
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+  asm("mov.u32 %0, %%lanemask_le;" : "=r"(le_mask));
 
   pdl_launch_dependents();  // a posterior launch behind this one may set up its shared memory early (it waits before reading K*)
   // ---- stage the evaluated set's dense tables once per (persistent) CTA: TMA bulk copies -> mbarrier
@@ -674,7 +676,14 @@ sot_pair_kernel(PairParams p, bosot_grammar g) {
 
 #pragma unroll 1
   for (int e = 2 * lane; e < e_pad; e += 64) *reinterpret_cast<uint2*>(acc + e) = make_uint2(0u, 0u);
-  auto claim = [&]() {
+  // (32-bit arithmetic on the low word of the counter while the pool and the grid together stay below 2^31 claims)
+  const bool small_claims = p.n_cand + n_warps_grid < 0x7fffffffLL;
+  auto claim = [&]() -> int64_t {
+    if (small_claims) {
+      uint32_t v = 0u;
+      if (lane == 0) v = atomicAdd(reinterpret_cast<unsigned int*>(p.next), 1u);
+      return (int64_t)((uint32_t)n_warps_grid + __shfl_sync(full, v, 0));
+    }
     unsigned long long v = 0ULL;
     if (lane == 0) v = atomicAdd(p.next, 1ULL);
     return n_warps_grid + (int64_t)__shfl_sync(full, v, 0);

@@ -26,16 +26,35 @@ y = np.random.default_rng(4).standard_normal(n_eval)
 eng = sot.AcquisitionEngine(ev, torch.from_numpy(y), gram, w, 1.3, 0.8, 1e-3, -0.5)
 off = 4096
 mine = torch.full((off + n,), -1.0, dtype=torch.float64, device=d0)
-peer = torch.full((off + n,), -1.0, dtype=torch.float64, device=d1)
 from bosot_b200 import _lib  # noqa: E402
 
+# The peer vector is a plain cudaMalloc block on cuda:1 (taken from the CUDA runtime directly: torch's caching allocator
+# may hand out virtual-memory mappings that cudaDeviceEnablePeerAccess does not cover; the product path uses torch
+# symmetric memory, one process per GPU, see bosot_b200/distributed.py).
+import ctypes as C  # noqa: E402
+import glob  # noqa: E402
+import os  # noqa: E402
+
+cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "lib", "libcudart*.so*")) + \
+    glob.glob(os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "cuda_runtime", "lib", "libcudart.so*")) + \
+    glob.glob("/usr/local/cuda/lib64/libcudart.so*")
+rt = C.CDLL(cands[0])
+nbytes = 8 * (off + n)
+peer_ptr = C.c_void_p()
+assert rt.cudaSetDevice(1) == 0
+assert rt.cudaMalloc(C.byref(peer_ptr), C.c_size_t(nbytes)) == 0
+assert rt.cudaMemset(peer_ptr, 0xFF, C.c_size_t(nbytes)) == 0  # all ones = NaN pattern: "not written"
+assert rt.cudaDeviceSynchronize() == 0
+assert rt.cudaSetDevice(0) == 0
 _lib.check(_lib.load().bosot_enable_peer_access(1), "enable_peer_access")  # cuda:0 maps cuda:1's memory
-torch.cuda.synchronize(d0), torch.cuda.synchronize(d1)
-table = torch.tensor([mine.data_ptr(), peer.data_ptr()], dtype=torch.int64, device=d0)
+torch.cuda.synchronize(d0)
+table = torch.tensor([mine.data_ptr(), peer_ptr.value], dtype=torch.int64, device=d0)
 plain = [t.clone() for t in eng.acquire_device(ca)]
 for _ in range(2):
     mu, sg, ei = eng.acquire_device(ca, scatter=(table.data_ptr(), 2, off))
 torch.cuda.synchronize(d0)
-ok = torch.equal(ei, plain[2]) and torch.equal(mine[off:], ei) and torch.equal(peer[off:].to(d0), ei) and bool((peer[:off] == -1).all())
+back = torch.empty(off + n, dtype=torch.float64, device=d0)
+assert rt.cudaMemcpy(C.c_void_p(back.data_ptr()), peer_ptr, C.c_size_t(nbytes), 4) == 0  # cudaMemcpyDefault
+ok = torch.equal(ei, plain[2]) and torch.equal(mine[off:], ei) and torch.equal(back[off:], ei) and bool(torch.isnan(back[:off]).all())
 print("scatter over NVLink: %d candidates x %d evaluated, %d bytes of EI to the peer per launch, bits %s" % (n, n_eval, 8 * n, "OK" if ok else "MISMATCH"))
 sys.exit(0 if ok else 1)
