@@ -83,3 +83,27 @@ def test_large_and_small_pools_take_the_same_route():
     K_small = sot.sot_pairs(sot.as_device_trees(ev_np, DEV), state, w, 1.3, 0.8)["K"]
     K_big = sot.sot_pairs(sot.as_device_trees(big, DEV), state, w, 1.3, 0.8)["K"]
     assert torch.equal(K_big[1000:1064], K_small)
+
+
+@pytest.mark.parametrize("gen,dim", [("CKSHighDimSearchSpace", 5), ("CKSHighDimSearchSpace", 3), ("CKSWithRQSearchSpace", 2)])
+def test_block_vector_cache_changes_no_bit(gen, dim):
+    """Pools beyond the fused-scan limit go through the two-launch path, where (for search spaces whose blocks have at most
+    two kinds) the DIM_WISE distances come from the per-CTA block-vector cache and only candidates with more than five
+    leaves of one kind build their own table; small pools never use the cache.  Same trees, same bits, for D_f, D and K."""
+    gram = Grammar.get(gen, dim)
+    ev_np = random_stress_trees(150, gram, seed=21)
+    big = random_stress_trees(20_000, gram, seed=22)
+    state = sot.EvalState(sot.as_device_trees(ev_np, DEV), gram)
+    w = np.array([0.3, 0.5, 0.2])
+    d_big = sot.as_device_trees(big, DEV)
+    whole = sot.sot_pairs(d_big, state, w, 0.9, 1.1, want=("K", "D", "Df"))
+    K_only = sot.sot_pairs(d_big, state, w, 0.9, 1.1)["K"]
+    assert torch.equal(K_only, whole["K"])
+    for c0 in range(0, 20_000, 5_000):  # 5000 rows: the fused-scan path, no cache
+        part = sot.sot_pairs(d_big[c0:c0 + 5_000].contiguous(), state, w, 0.9, 1.1, want=("K", "D", "Df"))
+        assert torch.equal(part["K"], whole["K"][c0:c0 + 5_000])
+        assert torch.equal(part["D"], whole["D"][c0:c0 + 5_000])
+        assert torch.equal(part["Df"], whole["Df"][:, c0:c0 + 5_000])
+    # the pool does contain candidates on the fallback route (a kind with more than five leaves)
+    n_leaves = (big[:, 0].astype(int) + 1) // 2
+    assert (n_leaves > 12).sum() > 100
