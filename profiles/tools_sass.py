@@ -11,7 +11,9 @@ LIB = os.path.join(ROOT, "bosot_b200", "libbosot_b200.so")
 # kernel label -> substring of the mangled name (resolved against the symbols of the built library)
 KERNELS = {
     "scan_kernel": "11scan_kernelE",
-    "sot_pair_kernel_R7": "15sot_pair_kernelILi7ELb0E",
+    "sot_pair_kernel_R7_table_exp": "15sot_pair_kernelILi7ELb0ELb0ELi1E",   # two-launch path, table-driven exp (the bench kernel)
+    "sot_pair_kernel_R2_fused_scan": "15sot_pair_kernelILi2ELb0ELb1ELi1E",  # small pools (10k x 50)
+    "sot_pair_kernel_R7_f32": "15sot_pair_kernelILi7ELb0ELb0ELi2E",         # fp32 outputs
     "posterior_ws_kernel_TC64": "19posterior_ws_kernelILi64E",
 }
 _symbols = [l.split("Function :")[1].strip() for l in subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout.splitlines()
@@ -32,4 +34,4 @@ for name, sym in KERNELS.items():
         for op, n in ops.most_common():
             f.write("#   %-28s %5d\n" % (op, n))
         f.write("\n".join(lines) + "\n")
-    print(path, len(lines), {k: ops[k] for k in ops if any(t in k for t in ("UBLKCP", "DMMA", "VIMNMX.U16x2", "REDUX", "MATCH", "SYNCS", "ATOMS"))})
+    print(path, len(lines), {k: ops[k] for k in ops if any(t in k for t in ("UBLKCP", "DMMA", "VIMNMX.U16x2", "REDUX", "MATCH", "SYNCS", "ATOMS", "MUFU.EX2"))})
