@@ -1,2 +1,13 @@
-"""Mirror of bosot/configs/kernels/kernel_grammar_generators/cks_with_rq_generator_config.py."""
-from .generator_configs import *  # noqa: F401,F403
+"""Generator config of the CKSWithRQSearchSpace: RBF, periodic, linear and RQ on every input dimension
+(bosot/configs/kernels/kernel_grammar_generators/cks_with_rq_generator_config.py:20-28)."""
+from .base_kernel_grammar_generator_config import BaseKernelGrammarGeneratorConfig
+
+
+class CKSWithRQGeneratorConfig(BaseKernelGrammarGeneratorConfig):
+    n_initial_factor_trailing = 5
+    n_exploration_trailing = 15
+    exploration_p_geometric = 1.0 / 3.0
+    n_exploitation_trailing = 50
+    walk_length_exploitation_trailing = 5
+    do_random_walk_exploitation_trailing = False
+    name = "CKSWithRQGenerator"

@@ -1,27 +1,5 @@
-"""bosot/configs/kernels/kernel_grammar_generators/*.py (all four share the same defaults)."""
-from .base_kernel_grammar_generator_config import BaseKernelGrammarGeneratorConfig
-
-
-class _TrailingDefaults(BaseKernelGrammarGeneratorConfig):
-    n_initial_factor_trailing = 5
-    n_exploration_trailing = 15
-    exploration_p_geometric = 1.0 / 3.0
-    n_exploitation_trailing = 50
-    walk_length_exploitation_trailing = 5
-    do_random_walk_exploitation_trailing = False
-
-
-class CKSWithRQGeneratorConfig(_TrailingDefaults):
-    name = "CKSWithRQGenerator"
-
-
-class CKSHighDimGeneratorConfig(_TrailingDefaults):
-    name = "CKSHighDimGenerator"
-
-
-class CompositionalKernelSearchGeneratorConfig(_TrailingDefaults):
-    name = "CompositionalKernelSearchGenerator"
-
-
-class NDimFullKernelsGrammarGeneratorConfig(_TrailingDefaults):
-    name = "NDimFullKernelsGrammarGenerator"
+"""The four generator configs in one namespace (one module each in the reference, mirrored next to this file)."""
+from .cks_high_dim_generator_config import CKSHighDimGeneratorConfig  # noqa: F401
+from .cks_with_rq_generator_config import CKSWithRQGeneratorConfig  # noqa: F401
+from .compositional_kernel_search_configs import CompositionalKernelSearchGeneratorConfig  # noqa: F401
+from .n_dim_full_kernels_generators_configs import NDimFullKernelsGrammarGeneratorConfig  # noqa: F401
