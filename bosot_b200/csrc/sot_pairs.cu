@@ -40,7 +40,11 @@ namespace bosot {
 
 int experiment_flag();
 
-constexpr int kMaxPairWarps = 28;   // one persistent CTA of up to 28 warps per SM (72 registers per thread; measured: 20 / 24 / 28 / 32 warps = 2.68 / 2.52 / 2.43 / 2.49 ms)
+// One persistent CTA of 32 warps per SM (64 registers per thread).  Round 1 measured 20 / 24 / 28 / 32 warps = 2.68 / 2.52 /
+// 2.43 / 2.49 ms at 1M x 200 and kept 28; with the leaner round-2 kernel 24 / 28 / 32 warps = 2.119 / 2.023 / 1.976 ms, and
+// the kernels with eight evaluated trees per lane (E > 224, a few spilled bytes either way) 0.495 / 0.480 ms at 200k x 256
+// for 28 / 32 warps (profiles/r3l_ab_warps.log).
+__host__ __device__ constexpr int pair_max_warps(int /*R*/) { return 32; }
 constexpr int kScanThreads = 128;
 // Block-vector cache of the DIM_WISE distances (state mode, blocks of at most two kinds): the vector of a candidate in
 // one block of input dimensions is fixed by the leaf counts (c1, c2) of the block's kinds, so L1(block vector, state)
@@ -499,7 +503,7 @@ __device__ __forceinline__ void store_out(double* base, size_t idx, double v) {
 }
 
 template <int R, bool kExtra, bool kFused, int kMode>
-__global__ void __launch_bounds__(kMaxPairWarps * 32, 1)
+__global__ void __launch_bounds__(pair_max_warps(R) * 32, 1)
 sot_pair_kernel(PairParams p, bosot_grammar g) {
   constexpr bool kFast = kMode == 1, kF32 = kMode == 2;
   using OutT = typename std::conditional<kF32, float, double>::type;
@@ -1058,7 +1062,10 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   }
 
   // launch 2: pairs.  One persistent CTA per SM; small pools shrink the CTA so that every SM gets warps.
-  int warps = kMaxPairWarps;
+  const int rounds = (n_eval + 31) / 32;  // evaluated trees per lane; beyond 256 trees: tiles of 256 (e_pad is a multiple of 256)
+  const int R = rounds < kMaxR ? rounds : kMaxR;
+  const int max_warps = pair_max_warps(R);
+  int warps = max_warps;
   while (warps > 1 && (n_cand + warps - 1) / warps < sms) warps >>= 1;
   StageLayout S = stage_layout(p.L.e_pad, grammar->n_dim_cols, grammar->n_symbols, grammar->n_blocks, fast);
   const size_t per_warp = warp_layout(p.L.e_pad, grammar->n_dim_cols, grammar->n_blocks, fused).total;
@@ -1083,8 +1090,6 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   }
 
   const bool extra = d_D != nullptr || d_Df != nullptr;
-  const int rounds = (n_eval + 31) / 32;  // evaluated trees per lane; beyond 256 trees: tiles of 256 (e_pad is a multiple of 256)
-  const int R = rounds < kMaxR ? rounds : kMaxR;
   using KernelFn = void (*)(PairParams, bosot_grammar);
 #define BOSOT_PAIR_X(r, x, f) {sot_pair_kernel<r, x, f, 0>, sot_pair_kernel<r, x, f, 1>, sot_pair_kernel<r, x, f, 2>}
 #define BOSOT_PAIR_ROW(r) {{BOSOT_PAIR_X(r, false, false), BOSOT_PAIR_X(r, false, true)}, {BOSOT_PAIR_X(r, true, false), BOSOT_PAIR_X(r, true, true)}}
@@ -1105,7 +1110,7 @@ int launch_pairs(const uint8_t* d_trees, int64_t n_cand, const bosot_grammar* gr
   if (int rc = cuda_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem),
                           "cudaOccupancyMaxActiveBlocksPerMultiprocessor")) return rc;
   if (per_sm < 1) per_sm = 1;
-  if (per_sm * warps > kMaxPairWarps) per_sm = kMaxPairWarps / warps;
+  if (per_sm * warps > max_warps) per_sm = max_warps / warps;
   const int64_t want = (n_cand + warps - 1) / warps;
   const int64_t wave = (int64_t)sms * per_sm;
   const int64_t grid = want < wave ? want : wave;
