@@ -329,11 +329,13 @@ posterior_ws_kernel(PostParams p) {
       const double* a_lo = a_up + (size_t)KS * 32;
       const double* bp = Kt + g * tld + t;
       const int nks_pad = (nks + kPD - 1) & ~(kPD - 1);
+      // L^-1 fragments are read once per tile and shared by nobody on this SM: ld.global.cg (L2 only) keeps them out of the
+      // small L1 that is left beside 210 KB of shared memory (1.644 -> 1.621 ms at 1M x 200 against ld.global.nc, on-box A/B)
       double ra_up[kPD], ra_lo[kPD], bf[2][NB];  // B fragments ping-pong between two register sets (kPD is even)
 #pragma unroll
       for (int u = 0; u < kPD; ++u) {
-        ra_up[u] = __ldg(a_up + 32 * u);
-        ra_lo[u] = lower_live ? __ldg(a_lo + 32 * u) : 0.0;
+        ra_up[u] = __ldcg(a_up + 32 * u);
+        ra_lo[u] = lower_live ? __ldcg(a_lo + 32 * u) : 0.0;
       }
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) bf[0][nb] = bp[(size_t)nb * 8 * tld];
@@ -345,8 +347,8 @@ posterior_ws_kernel(PostParams p) {
           const int ks = ks0 + u;
           const double au = ra_up[u], al = ra_lo[u];
           if (ks + kPD < nks_pad) {
-            ra_up[u] = __ldg(a_up + 32 * (ks + kPD));
-            ra_lo[u] = lower_live ? __ldg(a_lo + 32 * (ks + kPD)) : 0.0;
+            ra_up[u] = __ldcg(a_up + 32 * (ks + kPD));
+            ra_lo[u] = lower_live ? __ldcg(a_lo + 32 * (ks + kPD)) : 0.0;
           }
 #pragma unroll
           for (int nb = 0; nb < NB; ++nb) bf[(u + 1) & 1][nb] = bp[(size_t)nb * 8 * tld + 4 * (ks + 1)];
