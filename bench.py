@@ -306,7 +306,9 @@ def main() -> None:
                                            0.01, 3.0, mu.data_ptr(), sigma.data_ptr(), ei_local.data_ptr(), stream))
 
     ms_pairs = timed(k_pairs, args.steps, 3, collective=False)
+    spread_pairs = dict(timed.last)
     ms_post = timed(k_post, args.steps, 3, collective=False)
+    spread_post = dict(timed.last)
     clocks.__exit__()
 
     # Once per model update (every BO step) the evaluated-set state is rebuilt: inverted index, E x E Gram, Cholesky
@@ -556,6 +558,7 @@ def main() -> None:
         traffic=traffic, peak_source=peaks["source"],
         algorithmic_bytes_per_launch=alg_bytes, kernel_ms=dur,
         kernels_ms=dict(sot_pair_kernel=ms_pairs, posterior_kernel=ms_post),
+        kernels_ms_spread=dict(sot_pair_kernel=spread_pairs, posterior_kernel=spread_post),  # rank 0: median / min / max of the timed launches
         kernel_launches="sot_pair_kernel = scan_kernel + sot_pair_kernel (C-ABI bosot_sot_pairs); posterior_kernel = posterior_ws_kernel",
         note="fp64 issue, not HBM, is the practical ceiling of both kernels (DESIGN.md); secondary ceiling below",
         fp64=dict(measured_dfma_tflops=fp64_tflops, measured_dmma_tflops=dmma_tflops,
