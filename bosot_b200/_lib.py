@@ -127,6 +127,8 @@ SIGNATURES = {
     "bosot_neighbours": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, _P, _P]),
     "bosot_host_choices": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
     "bosot_host_recursive_dataset": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, C.c_int, _P, C.POINTER(C.c_int64)]),
+    "bosot_host_choices_cb": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
+    "bosot_host_recursive_dataset_cb": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, _P, C.POINTER(C.c_int64)]),
     "bosot_gp_fit_max_eval": (C.c_int, []),
     "bosot_gp_nll_grad": (C.c_int, [_P, C.c_int, C.c_int64, _P, _D3, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P]),
     "bosot_hellinger_record_doubles": (C.c_int, [C.c_int]),

@@ -80,14 +80,40 @@ __global__ void neighbour_kernel(const uint8_t* __restrict__ trees, int64_t n_tr
 // replayed here from a block of raw 32-bit outputs of NumPy's global generator: RandomState.choice(n) = randint(0, n)
 // = masked rejection on 32-bit outputs (mask = next power of two minus one, redraw while value > n - 1; no draw at
 // all for n == 1).  The caller advances the global generator by the number of outputs consumed.
-static inline bool legacy_choice(const uint32_t* raw, int64_t n_raw, int64_t& pos, int64_t n, int64_t& out) {
+// The raw outputs come either from a block the caller drew in advance (RawBlock: the caller restores the generator
+// and advances it by the number consumed) or straight from the generator through its C interface (RawCallback:
+// numpy.random.get_bit_generator().ctypes.next_uint32 -- the generator ends up exactly where the reference's sequence
+// of np.random.choice calls would have left it, no block, no save / restore).
+struct RawBlock {
+  const uint32_t* raw;
+  int64_t n_raw, pos;
+  __host__ bool next(uint32_t& v) {
+    if (pos >= n_raw) return false;
+    v = raw[pos++];
+    return true;
+  }
+};
+struct RawCallback {
+  bosot_next_u32_fn fn;
+  void* state;
+  int64_t pos;
+  __host__ bool next(uint32_t& v) {
+    v = fn(state);
+    ++pos;
+    return true;
+  }
+};
+
+template <class Src>
+static inline bool legacy_choice(Src& src, int64_t n, int64_t& out) {
   const uint64_t rng = (uint64_t)n - 1;
   if (rng == 0) { out = 0; return true; }
   uint64_t mask = rng;
   mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
   while (true) {
-    if (pos >= n_raw) return false;
-    const uint64_t v = raw[pos++] & mask;
+    uint32_t raw;
+    if (!src.next(raw)) return false;
+    const uint64_t v = raw & mask;
     if (v <= rng) { out = (int64_t)v; return true; }
   }
 }
@@ -97,29 +123,23 @@ static inline int64_t neighbour_count(const uint8_t* rec, int B) {  // kernel_gr
   return ((n + 1) / 2) * B + n * 2 * B;
 }
 
-}  // namespace bosot
-
-extern "C" int bosot_host_choices(const uint32_t* h_raw, int64_t n_raw, const int64_t* h_n, int64_t count, int64_t* h_out,
-                                  int64_t* h_consumed) {
-  using namespace bosot;
-  if (!h_raw || !h_n || !h_out || !h_consumed || n_raw < 0 || count < 0) return set_error(BOSOT_EINVAL, "bosot_host_choices: bad argument");
-  int64_t pos = 0;
-  for (int64_t i = 0; i < count; ++i) {
+template <class Src>
+static int host_choices(Src& src, const int64_t* h_n, int64_t count, int64_t* h_out, int64_t* h_consumed) {
+  if (!h_n || !h_out || !h_consumed || count < 0) return set_error(BOSOT_EINVAL, "bosot_host_choices: bad argument");
+  for (int64_t i = 0; i < count; ++i)
     if (h_n[i] < 1 || h_n[i] > 0x100000000LL) return set_error(BOSOT_EINVAL, "bosot_host_choices: population size out of range");
-    if (!legacy_choice(h_raw, n_raw, pos, h_n[i], h_out[i])) return BOSOT_ERAW;
-  }
-  *h_consumed = pos;
+  for (int64_t i = 0; i < count; ++i)
+    if (!legacy_choice(src, h_n[i], h_out[i])) return BOSOT_ERAW;
+  *h_consumed = src.pos;
   return BOSOT_OK;
 }
 
-extern "C" int bosot_host_recursive_dataset(const uint32_t* h_raw, int64_t n_raw, int n_symbols, int64_t n_data, int n_per_step,
-                                            uint8_t* h_pool, int64_t* h_consumed) {
-  using namespace bosot;
-  if (!h_raw || !h_pool || !h_consumed || n_raw < 0 || n_data < 0 || n_per_step < 1)
-    return set_error(BOSOT_EINVAL, "bosot_host_recursive_dataset: bad argument");
+template <class Src>
+static int host_recursive_dataset(Src& src, int n_symbols, int64_t n_data, int n_per_step, uint8_t* h_pool, int64_t* h_consumed) {
+  if (!h_pool || !h_consumed || n_data < 0 || n_per_step < 1) return set_error(BOSOT_EINVAL, "bosot_host_recursive_dataset: bad argument");
   if (n_symbols < 1 || n_symbols > BOSOT_MAX_SYMBOLS) return set_error(BOSOT_EINVAL, "bosot_host_recursive_dataset: n_symbols out of range");
   const int B = n_symbols;
-  int64_t len = 0, pos = 0;
+  int64_t len = 0;
   for (; len < B; ++len) {  // the roots: one leaf per base kernel
     uint8_t* r = h_pool + len * kTreeBytes;
     for (int q = 0; q < kTreeBytes; ++q) r[q] = BOSOT_PAD;
@@ -128,19 +148,49 @@ extern "C" int bosot_host_recursive_dataset(const uint32_t* h_raw, int64_t n_raw
   }
   while (len < n_data) {
     int64_t c = 0;
-    if (!legacy_choice(h_raw, n_raw, pos, len, c)) return BOSOT_ERAW;
+    if (!legacy_choice(src, len, c)) return BOSOT_ERAW;
     const uint8_t* chosen = h_pool + c * kTreeBytes;
     for (int s = 0; s < n_per_step && len < n_data; ++s) {
       int64_t k = 0;
-      if (!legacy_choice(h_raw, n_raw, pos, neighbour_count(chosen, B), k)) return BOSOT_ERAW;
+      if (!legacy_choice(src, neighbour_count(chosen, B), k)) return BOSOT_ERAW;
       const int st = neighbour_move(chosen, k, B, h_pool + len * kTreeBytes);
       if (st == BOSOT_NEIGHBOUR_TOO_BIG) return set_error(BOSOT_ETREE, "bosot_host_recursive_dataset: neighbour exceeds the 63-node flat record");
       if (st) return set_error(BOSOT_ETREE, "bosot_host_recursive_dataset: malformed record");
       ++len;
     }
   }
-  *h_consumed = pos;
+  *h_consumed = src.pos;
   return BOSOT_OK;
+}
+
+}  // namespace bosot
+
+extern "C" int bosot_host_choices(const uint32_t* h_raw, int64_t n_raw, const int64_t* h_n, int64_t count, int64_t* h_out,
+                                  int64_t* h_consumed) {
+  if (!h_raw || n_raw < 0) return bosot::set_error(BOSOT_EINVAL, "bosot_host_choices: bad argument");
+  bosot::RawBlock src{h_raw, n_raw, 0};
+  return bosot::host_choices(src, h_n, count, h_out, h_consumed);
+}
+
+extern "C" int bosot_host_choices_cb(bosot_next_u32_fn next_u32, void* rng_state, const int64_t* h_n, int64_t count, int64_t* h_out,
+                                     int64_t* h_consumed) {
+  if (!next_u32) return bosot::set_error(BOSOT_EINVAL, "bosot_host_choices_cb: null generator callback");
+  bosot::RawCallback src{next_u32, rng_state, 0};
+  return bosot::host_choices(src, h_n, count, h_out, h_consumed);
+}
+
+extern "C" int bosot_host_recursive_dataset(const uint32_t* h_raw, int64_t n_raw, int n_symbols, int64_t n_data, int n_per_step,
+                                            uint8_t* h_pool, int64_t* h_consumed) {
+  if (!h_raw || n_raw < 0) return bosot::set_error(BOSOT_EINVAL, "bosot_host_recursive_dataset: bad argument");
+  bosot::RawBlock src{h_raw, n_raw, 0};
+  return bosot::host_recursive_dataset(src, n_symbols, n_data, n_per_step, h_pool, h_consumed);
+}
+
+extern "C" int bosot_host_recursive_dataset_cb(bosot_next_u32_fn next_u32, void* rng_state, int n_symbols, int64_t n_data, int n_per_step,
+                                               uint8_t* h_pool, int64_t* h_consumed) {
+  if (!next_u32) return bosot::set_error(BOSOT_EINVAL, "bosot_host_recursive_dataset_cb: null generator callback");
+  bosot::RawCallback src{next_u32, rng_state, 0};
+  return bosot::host_recursive_dataset(src, n_symbols, n_data, n_per_step, h_pool, h_consumed);
 }
 
 extern "C" int bosot_neighbours(const uint8_t* d_trees, int64_t n_trees, const int64_t* d_index, int n_symbols,

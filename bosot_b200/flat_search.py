@@ -87,12 +87,28 @@ def raise_on_neighbour_status(statuses) -> None:
             raise ValueError("bosot_b200: neighbour move failed at row %d (code %d)" % (i, int(status[i])))
 
 
+def _global_bitgen():
+    """(next_uint32 function pointer, state pointer) of NumPy's GLOBAL generator through the bit generator's ctypes
+    interface, or None when this NumPy cannot hand it out (then the block replay below is used)."""
+    get = getattr(np.random, "get_bit_generator", None)
+    if get is None:
+        return None
+    try:
+        iface = get().ctypes
+        return C.cast(iface.next_uint32, C.c_void_p), iface.state
+    except Exception:
+        return None
+
+
 def _replay_global_rng(call, expected_outputs: int):
     """Run ``call(raw_ptr, n_raw, consumed_ref) -> rc`` on a block of raw 32-bit outputs of NumPy's GLOBAL generator and
     leave the generator exactly where the reference's sequence of ``np.random.choice`` calls would have left it:
     the state is saved, a block of outputs is drawn, the C side reports how many it used, the state is restored and
     advanced by that many outputs.  The block grows until it is long enough (BOSOT_ERAW)."""
-    n_raw = max(64, 4 * int(expected_outputs))
+    # a block only a little longer than what is expected to be used: drawing (and re-drawing, below) raw outputs is
+    # the larger part of the host time of these producers (0.62 of 1.7 ms per 10k-candidate population with a block
+    # four times too long); a block that turns out too short costs one retry
+    n_raw = max(64, int(1.2 * expected_outputs) + 64)
     while True:
         state = np.random.get_state()
         raw = np.random.randint(0, 2**32, size=n_raw, dtype=np.uint32)
@@ -116,8 +132,14 @@ def legacy_choices(sizes: np.ndarray) -> np.ndarray:
     if len(sizes) == 0:
         return out
     lib = _lib.load()
+    gen = _global_bitgen()
+    if gen is not None:  # the draws come straight out of the global generator, which ends up where the reference's would
+        used = C.c_int64(0)
+        _lib.check(lib.bosot_host_choices_cb(gen[0], gen[1], sizes.ctypes.data, len(sizes), out.ctypes.data, C.byref(used)), "host_choices")
+        return out
+    # RandomState.choice(n) is a masked rejection on raw outputs: between 1 and 2 draws per choice on average
     _replay_global_rng(lambda raw, n_raw, used: lib.bosot_host_choices(raw, n_raw, sizes.ctypes.data, len(sizes), out.ctypes.data, used),
-                       2 * len(sizes))
+                       1.5 * len(sizes))
     return out
 
 
@@ -140,8 +162,14 @@ class FlatCandidateGenerator:
         B = self.grammar.n_symbols
         pool = np.empty((max(int(n_data), B), _lib.TREE_BYTES), dtype=np.uint8)
         lib = _lib.load()
+        gen = _global_bitgen()
+        if gen is not None:
+            used = C.c_int64(0)
+            _lib.check(lib.bosot_host_recursive_dataset_cb(gen[0], gen[1], B, int(n_data), int(n_per_step), pool.ctypes.data, C.byref(used)),
+                       "host_recursive_dataset")
+            return pool
         _replay_global_rng(lambda raw, n_raw, used: lib.bosot_host_recursive_dataset(raw, n_raw, B, int(n_data), int(n_per_step),
-                                                                                      pool.ctypes.data, used), 4 * int(n_data))
+                                                                                      pool.ctypes.data, used), 3.1 * int(n_data))
         return pool
 
     def get_initial_for_evolutionary_opt(self, n_initial: int) -> np.ndarray:

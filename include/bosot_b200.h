@@ -29,7 +29,7 @@
  *   bosot_topk_f64, bosot_argmax_f64  EvolutionaryOptimizerObjects.select / np.argmax on the device
  *                               (bayesian_optimization/evolutionary_optimizer_objects.py:42-44,57-64)
  *   bosot_gp_nll_grad ......... GPR.training_loss + gradient for the ML-II fit (models/gp_model.py:162-199)
- *   bosot_neighbours, bosot_host_choices, bosot_host_recursive_dataset
+ *   bosot_neighbours, bosot_host_choices(_cb), bosot_host_recursive_dataset(_cb)
  *                               the candidate producers (kernels/kernel_grammar/kernel_grammar_search_spaces.py:97-151,
  *                               kernel_grammar_candidate_generator.py:85-111)
  *   bosot_hellinger_* ......... the alternative kernel-kernel (kernels/kernel_kernel_hellinger.py:104-259)
@@ -349,6 +349,15 @@ int bosot_host_choices(const uint32_t* h_raw, int64_t n_raw, const int64_t* h_n,
                        int64_t* h_consumed);
 int bosot_host_recursive_dataset(const uint32_t* h_raw, int64_t n_raw, int n_symbols, int64_t n_data, int n_per_step,
                                  uint8_t* h_pool, int64_t* h_consumed);
+/* The same two producers pulling their raw outputs straight from the generator: next_u32(rng_state) must return the
+ * generator's next raw 32-bit output (NumPy: g = numpy.random.get_bit_generator().ctypes; next_u32 = g.next_uint32,
+ * rng_state = g.state).  The generator is left exactly where the reference's np.random.choice calls would have left
+ * it -- no block of outputs, no state to restore; *h_consumed = outputs drawn.  A validation failure draws nothing. */
+typedef uint32_t (*bosot_next_u32_fn)(void* rng_state);
+int bosot_host_choices_cb(bosot_next_u32_fn next_u32, void* rng_state, const int64_t* h_n, int64_t count, int64_t* h_out,
+                          int64_t* h_consumed);
+int bosot_host_recursive_dataset_cb(bosot_next_u32_fn next_u32, void* rng_state, int n_symbols, int64_t n_data, int n_per_step,
+                                    uint8_t* h_pool, int64_t* h_consumed);
 
 /* ---- Hellinger kernel-kernel --------------------------------------------------
  * The alternative kernel-kernel behind the same BaseObjectKernel API (reference

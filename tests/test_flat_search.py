@@ -134,6 +134,45 @@ def test_native_producers_error_behaviour():
     assert b"63-node" in lib.bosot_last_error()
 
 
+def test_generator_callback_and_block_replay_agree(monkeypatch):
+    """The producers pull their raw outputs straight from NumPy's global bit generator (bosot_host_*_cb, the default) or,
+    when this NumPy does not hand out the generator's C interface, replay a block drawn in advance: same records, same
+    indices, same generator state either way; a rejected call draws nothing."""
+    import ctypes as C
+
+    from bosot_b200 import _lib, flat_search as fs
+
+    assert fs._global_bitgen() is not None  # NumPy >= 1.24 here: the default route is the callback
+    gram = Grammar.get("CKSHighDimSearchSpace", 5)
+    g = FlatCandidateGenerator(gram)
+    sizes = np.random.default_rng(2).integers(1, 900, 5000)
+
+    def run():
+        np.random.seed(21)
+        pool = g.get_dataset_recursivly_generated(3000, 2)
+        idx = fs.legacy_choices(sizes)
+        return pool, idx, np.random.randint(0, 2**32, dtype=np.uint32)
+
+    a = run()
+    monkeypatch.setattr(fs, "_global_bitgen", lambda: None)
+    b = run()
+    monkeypatch.undo()
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+
+    lib = _lib.load()
+    out, used = np.empty(3, dtype=np.int64), C.c_int64(0)
+    ok = np.array([5, 7, 9], dtype=np.int64)
+    assert lib.bosot_host_choices_cb(None, None, ok.ctypes.data, 3, out.ctypes.data, C.byref(used)) == -1  # null callback
+    fn, st = fs._global_bitgen()
+    bad = np.array([5, 0, 9], dtype=np.int64)
+    np.random.seed(1)
+    before = np.random.get_state()[2]
+    assert lib.bosot_host_choices_cb(fn, st, bad.ctypes.data, 3, out.ctypes.data, C.byref(used)) == -1  # a size of 0: nothing is drawn
+    assert np.random.get_state()[2] == before
+    pool = np.empty((8, 64), dtype=np.uint8)
+    assert lib.bosot_host_recursive_dataset_cb(None, None, 3, 8, 1, pool.ctypes.data, C.byref(used)) == -1
+
+
 @pytest.mark.gpu
 def test_device_moves_match_host():
     torch = pytest.importorskip("torch")
