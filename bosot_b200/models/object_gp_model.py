@@ -16,6 +16,8 @@ consumes the global ``np.random`` stream the same way.
 """
 from __future__ import annotations
 
+import contextlib
+
 import copy
 import logging
 from typing import List, Optional, Tuple
@@ -202,16 +204,23 @@ class ObjectGpModel:
                 w3[g] += a / S
         else:  # a kernel-kernel with a single distance plane (Hellinger)
             w3 = [float(x) for x in k.device_weights()]
-        Df, y = self.model["Df"], self.model["y"]
         # The nine results go straight into PINNED HOST memory: under unified addressing the kernel stores to the host
         # pointer itself, so an evaluation is one launch + one stream synchronisation (no device buffer, no copy call).
         if getattr(self, "_fit_out", None) is None:
             self._fit_out = torch.zeros(9, dtype=torch.float64).pin_memory()
             self._fit_out_np = self._fit_out.numpy()
-        stream = torch.cuda.current_stream(Df.device)
-        with torch.cuda.device(Df.device):
-            rc = _lib.load().bosot_gp_nll_grad(Df.data_ptr(), Df.shape[1], Df.stride(1), y.data_ptr(), (C.c_double * 3)(*w3), ls, var, noise, c,
-                                               self._fit_out.data_ptr(), stream.cuda_stream)
+            self._fit_out_ptr = self._fit_out.data_ptr()
+        ctx = getattr(self, "_fit_ctx", None)
+        if ctx is not None:
+            # inside optimize(): the device guard, the stream and the raw pointers were taken once for the whole L-BFGS run
+            fn, stream, df_ptr, n_e, ld, y_ptr = ctx
+            rc = fn(df_ptr, n_e, ld, y_ptr, (C.c_double * 3)(*w3), ls, var, noise, c, self._fit_out_ptr, stream.cuda_stream)
+        else:
+            Df, y = self.model["Df"], self.model["y"]
+            stream = torch.cuda.current_stream(Df.device)
+            with torch.cuda.device(Df.device):
+                rc = _lib.load().bosot_gp_nll_grad(Df.data_ptr(), Df.shape[1], Df.stride(1), y.data_ptr(), (C.c_double * 3)(*w3), ls, var, noise, c,
+                                                   self._fit_out_ptr, stream.cuda_stream)
         _lib.check(rc, "gp_nll_grad")
         stream.synchronize()
         out = self._fit_out_np.tolist()
@@ -322,7 +331,8 @@ class ObjectGpModel:
                 layout, theta0, items = self._pack()
                 if len(theta0) == 0:
                     return
-                res = minimize(lambda th: self._loss_and_grad(th, layout), theta0, jac=True, method="L-BFGS-B")
+                with self._fit_context():
+                    res = minimize(lambda th: self._loss_and_grad(th, layout), theta0, jac=True, method="L-BFGS-B")
                 self._unpack(res.x, items)
                 success = bool(res.success)
             except Exception:  # noqa: BLE001 -- mirrors the reference's bare except
@@ -333,6 +343,25 @@ class ObjectGpModel:
                 return
             logger.warning("Not converged - try again")
             self.pertube_parameters(pertubation_factor)
+
+    @contextlib.contextmanager
+    def _fit_context(self):
+        """What every loss evaluation of one L-BFGS run needs and none of them changes: the CUDA device guard, the current
+        stream, the entry point and the raw pointers of the distance planes and targets (~10 us per evaluation otherwise,
+        ~50 evaluations per model update)."""
+        Df = None if self.model is None else self.model.get("Df")
+        fused = (Df is not None and self.use_fused_fit and Df.is_cuda and Df.shape[1] <= _lib.load().bosot_gp_fit_max_eval())
+        if not fused:
+            yield
+            return
+        y = self.model["y"]
+        with torch.cuda.device(Df.device):
+            self._fit_ctx = (_lib.load().bosot_gp_nll_grad, torch.cuda.current_stream(Df.device), Df.data_ptr(), Df.shape[1], Df.stride(1),
+                             y.data_ptr())
+            try:
+                yield
+            finally:
+                self._fit_ctx = None
 
     def multi_start_optimization(self, n_starts: int, pertubation_factor: float):
         """gp_model.py:201-245: best of n_starts perturbed fits by final loss."""
