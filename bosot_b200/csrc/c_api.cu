@@ -33,7 +33,12 @@ bool pdl_enabled() {
   static const bool on = std::getenv("BOSOT_NO_PDL") == nullptr;
   return on;
 }
-int experiment_flag() {  // BOSOT_EXPERIMENT=<int>: measurement switches of kernels under development (0 = product path)
+// BOSOT_EXPERIMENT=<bit mask>: measurement switches for A/B runs (0 = product path).  Bits in use (csrc/sot_pairs.cu):
+//   2  two-launch path (scan_kernel + pair kernel) also for pools up to the fused-scan limit
+//   4  general exp_nonpos route even when the hyper-parameters would allow the table-driven exp
+//   8  no block-vector cache of the DIM_WISE distances
+// None of them changes a result beyond the last bits of exp (bit 4); bits 2 and 8 are bit-identical to the product path.
+int experiment_flag() {
   static const int v = std::getenv("BOSOT_EXPERIMENT") ? std::atoi(std::getenv("BOSOT_EXPERIMENT")) : 0;
   return v;
 }
