@@ -92,6 +92,7 @@ SIGNATURES = {
          _P, C.c_size_t, _P, _P, _P, _P, _P],
     ),
     "bosot_pack_linv": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P]),
+    "bosot_gp_factorize": (C.c_int, [_P, C.c_int, C.c_int64, C.c_double, _P, _P, C.c_int, _P, _P, _P]),
     "bosot_max_f64": (C.c_int, [_P, C.c_int64, _P, _P]),
     "bosot_acquire_work_bytes": (C.c_size_t, [C.c_int64, C.c_int]),
     "bosot_acquire_host": (

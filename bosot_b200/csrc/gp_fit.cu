@@ -184,9 +184,123 @@ gp_nll_grad_kernel(FitParams p) {
   }
 }
 
+// ---- factorisation for the posterior: L^-1 (packed for the posterior kernel) and beta in ONE launch ------------
+// What sot.gp_factorize otherwise takes from cuSOLVER / cuBLAS in six launches and a synchronisation (potrf, a
+// triangular solve against the identity, the fragment-major packing, two triangular solves for beta): for evaluated
+// sets that fit the shared-memory Cholesky of the fit kernel (E <= kFitMaxE) the same sweep -- factorisation fused
+// with the inversion of the factor -- runs once per model update here, and the results leave the kernel in the
+// layout the posterior kernel reads (bosot_pack_linv).  Larger sets keep the library route.
+struct FactorParams {
+  const double* K;   // [E][ld] Gram of the evaluated set (lower triangle read)
+  int E;
+  int64_t ld;
+  double noise;
+  const double* err; // [E] y - c
+  double* LinvF;     // [ldl * ldl] fragment-major, zero padded
+  int ldl;
+  double* beta;      // [E] (K + noise I)^-1 err
+  int32_t* info;     // 0, or k + 1 when the leading minor k is not positive definite (device or mapped host memory)
+};
+
+template <int kFitTile>
+__global__ void __launch_bounds__(kFitTile * kFitTile)
+gp_factor_kernel(FactorParams p) {
+  constexpr int kFitThreads = kFitTile * kFitTile;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int E = p.E, lda = E | 1;
+  double* A = reinterpret_cast<double*>(smem);  // [E][lda]: lower = L, strict upper = (L^-1)^T
+  double* r = A + (size_t)E * lda;
+  double* z = r + E;
+  double* dinv = z + E;
+  __shared__ int s_info;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_info = 0;
+  const int tx = tid & (kFitTile - 1), ty = tid / kFitTile;
+  for (int i = ty; i < E; i += kFitTile)
+    for (int j = tx; j < E; j += kFitTile)
+      A[i * lda + j] = j <= i ? p.K[(size_t)i * p.ld + j] + (i == j ? p.noise : 0.0) : 0.0;
+  for (int i = tid; i < E; i += kFitThreads) r[i] = p.err[i];
+  __syncthreads();
+  // the sweep of gp_nll_grad_kernel: trailing Cholesky update + forward substitution of L Y = I, one barrier per column
+  for (int k = 0; k < E; ++k) {
+    const double dk = A[k * lda + k];
+    if (!(dk > 0.0)) {
+      if (tid == 0) s_info = k + 1;
+      break;
+    }
+    const double inv = 1.0 / dk;
+    for (int i = k + 1 + ty; i < E; i += kFitTile) {
+      const double lik = A[i * lda + k] * inv;
+      for (int j = k + 1 + tx; j <= i; j += kFitTile) A[i * lda + j] -= lik * A[j * lda + k];
+    }
+    for (int j = ty; j <= k; j += kFitTile) {
+      const double c = (j == k ? 1.0 : A[j * lda + k]) * inv;
+      for (int i = k + 1 + tx; i < E; i += kFitTile) A[j * lda + i] -= A[i * lda + k] * c;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (s_info != 0) {
+    if (tid == 0) *p.info = s_info;
+    return;
+  }
+  for (int k = tid; k < E; k += kFitThreads) dinv[k] = 1.0 / sqrt(A[k * lda + k]);
+  __syncthreads();
+  for (int j = ty; j < E; j += kFitTile)
+    for (int i = j + 1 + tx; i < E; i += kFitTile) A[j * lda + i] *= dinv[i];  // A[j][i] = L^-1[i][j], i > j
+  __syncthreads();
+  for (int i = tid; i < E; i += kFitThreads) {  // z = L^-1 err
+    double v = dinv[i] * r[i];
+    for (int j = 0; j < i; ++j) v += A[j * lda + i] * r[j];
+    z[i] = v;
+  }
+  __syncthreads();
+  for (int j = tid; j < E; j += kFitThreads) {  // beta = L^-T z
+    double a = dinv[j] * z[j];
+    for (int i = j + 1; i < E; ++i) a += A[j * lda + i] * z[i];
+    p.beta[j] = a;
+  }
+  // fragment-major packing (bosot_pack_linv): LinvF[(rb * ldl/4 + ks) * 32 + 4 g + t] = Linv[8 rb + g][4 ks + t]
+  const int KS = p.ldl >> 2;
+  for (int x = tid; x < p.ldl * p.ldl; x += kFitThreads) {
+    const int l = x & 31, f = x >> 5;
+    const int rb = f / KS, ks = f - rb * KS;
+    const int i = 8 * rb + (l >> 2), j = 4 * ks + (l & 3);
+    double v = 0.0;
+    if (i < E && j < E && j <= i) v = i == j ? dinv[i] : A[j * lda + i];
+    p.LinvF[x] = v;
+  }
+  if (tid == 0) *p.info = 0;
+}
+
 }  // namespace bosot
 
 extern "C" int bosot_gp_fit_max_eval(void) { return bosot::kFitMaxE; }
+
+extern "C" int bosot_gp_factorize(const double* d_K, int n_eval, int64_t ld, double noise_variance, const double* d_err,
+                                  double* d_LinvF, int ldl, double* d_beta, int32_t* info, void* stream) {
+  using namespace bosot;
+  if (!d_K || !d_err || !d_LinvF || !d_beta || !info) return set_error(BOSOT_EINVAL, "bosot_gp_factorize: null argument");
+  if (n_eval < 1 || n_eval > kFitMaxE || ld < n_eval) return set_error(BOSOT_EINVAL, "bosot_gp_factorize: n_eval out of range (see bosot_gp_fit_max_eval)");
+  if (ldl < n_eval || (ldl % 16) != 0) return set_error(BOSOT_EINVAL, "bosot_gp_factorize: ldl must be a multiple of 16 and >= n_eval");
+  FactorParams p;
+  p.K = d_K; p.E = n_eval; p.ld = ld; p.noise = noise_variance; p.err = d_err;
+  p.LinvF = d_LinvF; p.ldl = ldl; p.beta = d_beta; p.info = info;
+  const size_t smem = sizeof(double) * ((size_t)n_eval * (n_eval | 1) + 3 * (size_t)n_eval);
+  static std::atomic<bool> attr_set[64];  // zero-initialised; the (idempotent) set-up may run twice under a race, never zero times
+  int dev = 0;
+  if (int rc = cuda_check(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+  if (!(dev < 64 && attr_set[dev])) {
+    if (int rc = cuda_check(cudaFuncSetAttribute(gp_factor_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024),
+                            "cudaFuncSetAttribute(gp_factor_kernel<16>)")) return rc;
+    if (int rc = cuda_check(cudaFuncSetAttribute(gp_factor_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024),
+                            "cudaFuncSetAttribute(gp_factor_kernel<32>)")) return rc;
+    if (dev < 64) attr_set[dev] = true;
+  }
+  if (n_eval <= 48) gp_factor_kernel<16><<<1, 256, smem, (cudaStream_t)stream>>>(p);
+  else gp_factor_kernel<32><<<1, 1024, smem, (cudaStream_t)stream>>>(p);
+  return after_launch("gp_factor_kernel");
+}
 
 extern "C" int bosot_gp_nll_grad(const double* d_Df, int n_eval, int64_t ld, const double* d_y, const double weights[3],
                                  double lengthscale, double variance, double noise_variance, double mean_c,

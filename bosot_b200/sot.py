@@ -195,13 +195,43 @@ def sot_pairs(
 
 
 # ------------------------------------------------------------------------- GP factorisation
+_INFO = {}
+
+
+def _pinned_info(dev) -> torch.Tensor:
+    """One pinned int32 per device for the status word of bosot_gp_factorize (the kernel stores into it directly)."""
+    key = str(dev)
+    if key not in _INFO:
+        _INFO[key] = torch.zeros(1, dtype=torch.int32).pin_memory()
+    return _INFO[key]
+
+
 def gp_factorize(K_EE: torch.Tensor, noise_variance: float, err: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Small E x E part of the posterior, left to cuSOLVER/cuBLAS via torch.linalg:
+    """Small E x E part of the posterior: one fused launch for evaluated sets that fit the shared-memory Cholesky
+    (``bosot_gp_factorize``, E <= 160), else left to cuSOLVER/cuBLAS via torch.linalg:
     Lm = chol(K_EE + s^2 I) (GPflow ``base_conditional``), returns
     (LinvF = Lm^-1 packed by ``bosot_pack_linv`` into the zero-padded fragment-major layout of order
     ldl (multiple of 16) that the posterior kernel's fp64 tensor-core tiles read, beta = (K_EE + s^2 I)^-1 err).
     Raises like the reference's TF Cholesky when the matrix is not positive definite."""
     E = K_EE.shape[0]
+    lib = _lib.load()
+    if E <= lib.bosot_gp_fit_max_eval() and K_EE.stride(1) == 1:
+        # one launch (C-ABI bosot_gp_factorize): Cholesky fused with the inversion of the factor in shared memory, LinvF
+        # packed and beta written by the same kernel, the status into pinned host memory
+        dev = K_EE.device
+        ldl = (E + 15) // 16 * 16
+        Linv = torch.empty((ldl, ldl), dtype=torch.float64, device=dev)
+        beta = torch.empty(E, dtype=torch.float64, device=dev)
+        err = err.reshape(E).contiguous()
+        info = _pinned_info(dev)
+        stream = torch.cuda.current_stream(dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.bosot_gp_factorize(K_EE.data_ptr(), E, K_EE.stride(0), float(noise_variance), err.data_ptr(), Linv.data_ptr(), ldl,
+                                              beta.data_ptr(), info.data_ptr(), stream.cuda_stream), "gp_factorize")
+        stream.synchronize()
+        if int(info[0]) != 0:
+            raise RuntimeError("Cholesky decomposition was not successful (leading minor %d not positive definite)" % int(info[0]))
+        return Linv, beta
     A = K_EE + noise_variance * torch.eye(E, dtype=torch.float64, device=K_EE.device)
     L, info = torch.linalg.cholesky_ex(A)
     if int(info) != 0:

@@ -197,6 +197,16 @@ int bosot_posterior_acq(const double* d_Kstar, int64_t n_cand, int64_t ld, int n
                         int acq_kind, const double* d_current_max, double xi, double ucb_beta,
                         double* d_mu, double* d_sigma, double* d_acq, void* stream);
 
+/* What bosot_posterior_acq needs from the evaluated set, in ONE launch, for n_eval <= bosot_gp_fit_max_eval():
+ * Cholesky of K_EE + noise_variance * I fused with the inversion of the factor, LinvF in the packed layout above
+ * (order ldl, a multiple of 16, >= n_eval) and beta = (K_EE + noise_variance * I)^-1 err (err = y - mean_c).
+ * d_K: [n_eval][ld] Gram of the evaluated set (lower triangle read).  *info (device memory, or host memory the device
+ * can write: pinned) = 0, or k + 1 when the leading minor k is not positive definite -- the outputs are then undefined,
+ * like a failed tf.linalg.cholesky in the reference (models/gp_model.py:183-186 retries).  Larger evaluated sets take
+ * cuSOLVER / cuBLAS and bosot_pack_linv. */
+int bosot_gp_factorize(const double* d_K, int n_eval, int64_t ld, double noise_variance, const double* d_err,
+                       double* d_LinvF, int ldl, double* d_beta, int32_t* info, void* stream);
+
 /* max of n doubles into a device scalar (NaNs ignored like fmax) */
 int bosot_max_f64(const double* d_x, int64_t n, double* d_out, void* stream);
 

@@ -420,3 +420,36 @@ def test_bic_mean_in_the_model_and_the_bo_loop():
     np.testing.assert_allclose(acq[ok], (dd * _norm.cdf(dd / sigma) + sigma * _norm.pdf(dd / sigma))[ok], rtol=1e-9)
     _, queries, *_ = bo.maximize(1)
     assert len(queries) == 1
+
+
+@pytest.mark.parametrize("n_eval", [1, 7, 16, 17, 50, 100, 160])
+def test_fused_factorisation_matches_the_library_route(n_eval):
+    """bosot_gp_factorize (one launch: Cholesky + inverse of the factor + packing + beta) against cuSOLVER / cuBLAS through
+    torch.linalg on the same matrix: L^-1 and beta to 1e-9 relative of their scale; a matrix that is not positive definite
+    raises like the library route (and like the reference's tf.linalg.cholesky, which the fit loop retries)."""
+    from bosot_b200 import _lib, sot
+
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(40 + n_eval)
+    X = torch.rand((n_eval, 5), dtype=torch.float64, device=dev, generator=g)
+    K = 1.3 * torch.exp(-torch.cdist(X, X, p=1.0) / 0.64)
+    err = torch.randn(n_eval, dtype=torch.float64, device=dev, generator=g)
+    noise = 1e-3
+    Linv, beta = sot.gp_factorize(K, noise, err)  # fused route (n_eval <= bosot_gp_fit_max_eval())
+    L = torch.linalg.cholesky(K + noise * torch.eye(n_eval, dtype=torch.float64, device=dev))
+    Linv_ref = torch.linalg.solve_triangular(L, torch.eye(n_eval, dtype=torch.float64, device=dev), upper=False)
+    beta_ref = torch.cholesky_solve(err.reshape(-1, 1), L).reshape(-1)
+    ldl = (n_eval + 15) // 16 * 16
+    packed_ref = torch.empty((ldl, ldl), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().bosot_pack_linv(Linv_ref.contiguous().data_ptr(), n_eval, n_eval, packed_ref.data_ptr(), ldl,
+                                               torch.cuda.current_stream().cuda_stream), "pack_linv")
+    scale = float(Linv_ref.abs().max())
+    assert float((Linv - packed_ref).abs().max()) <= 1e-9 * scale
+    assert float((beta - beta_ref).abs().max()) <= 1e-9 * float(beta_ref.abs().max() + 1.0)
+    # the padding of the packed layout is zero (the posterior kernel multiplies it)
+    assert float(Linv.abs().sum()) > 0 and torch.isfinite(Linv).all()
+    bad = K.clone()
+    bad[n_eval // 2, n_eval // 2] = -5.0
+    with pytest.raises(RuntimeError, match="not positive definite"):
+        sot.gp_factorize(bad, noise, err)
